@@ -1,0 +1,83 @@
+"""ctypes binding of libaligner_b200.so (the C ABI declared in include/aligner_b200.h).
+
+There is no CPU fallback: if the shared library is missing this module raises at
+import time, and every entry point fails loudly without an sm_100 device.
+"""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libaligner_b200.so"
+
+OK = 0
+E_INVALID, E_UNSUPPORTED, E_CUDA, E_LENGTHS, E_NO_DEVICE = -1, -2, -3, -4, -5
+
+# mask element types (ALB200_* in the header)
+F32, F16, BF16, F64, U8, I8, I16, I32, I64 = range(9)
+
+# every symbol include/aligner_b200.h declares (tests check the export list against the header)
+SYMBOLS = (
+    "alb200_last_error", "alb200_version", "alb200_mas_device", "alb200_mas_device_masked",
+    "alb200_mas_workspace_bytes", "alb200_mas_status", "alb200_maximum_path_c",
+    "alb200_last_transfer_bytes", "alb200_launch_count",
+)
+
+
+class AlignerB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("aligner_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _load() -> ctypes.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            "%s not found: build it with `python -m aligner_b200.build` "
+            "(aligner_b200 has no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(str(LIB_PATH))
+    vp, i32, i64, u64, f32, sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64,
+                                  ctypes.c_float, ctypes.c_size_t)
+    lib.alb200_last_error.restype = ctypes.c_char_p
+    lib.alb200_version.restype = ctypes.c_char_p
+    lib.alb200_launch_count.restype = u64
+    lib.alb200_last_transfer_bytes.argtypes = [ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    lib.alb200_last_transfer_bytes.restype = None
+    lib.alb200_mas_device.argtypes = [vp, vp, vp, vp, i32, u64, i32, vp, vp, i32, i32, i32, f32, vp, sz, vp]
+    lib.alb200_mas_device.restype = i32
+    lib.alb200_mas_device_masked.argtypes = [vp, vp, i32, i64, i64, i64, vp, i32, u64, i32, vp, vp, vp,
+                                             i32, i32, i32, f32, vp, sz, vp]
+    lib.alb200_mas_device_masked.restype = i32
+    lib.alb200_mas_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.alb200_mas_workspace_bytes.restype = sz
+    lib.alb200_mas_status.argtypes = [vp, vp]
+    lib.alb200_mas_status.restype = i32
+    lib.alb200_maximum_path_c.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32]
+    lib.alb200_maximum_path_c.restype = i32
+    if hasattr(lib, "alb200_neg_cent_gaussian"):
+        lib.alb200_neg_cent_gaussian.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
+        lib.alb200_neg_cent_gaussian.restype = i32
+        lib.alb200_neg_cent_ota.argtypes = [vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, i32, vp, sz, vp]
+        lib.alb200_neg_cent_ota.restype = i32
+        lib.alb200_neg_cent_workspace_bytes.argtypes = [i32, i32, i32, i32]
+        lib.alb200_neg_cent_workspace_bytes.restype = sz
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise AlignerB200Error(rc, lib.alb200_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(lib.alb200_launch_count())
+
+
+def last_transfer_bytes() -> tuple[int, int]:
+    a, b = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    lib.alb200_last_transfer_bytes(ctypes.byref(a), ctypes.byref(b))
+    return int(a.value), int(b.value)

@@ -1,0 +1,69 @@
+"""Build libaligner_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m aligner_b200.build [--force] [--verbose]
+
+The shared library is the product's only compute path; nothing here builds or
+links the CPU oracle.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libaligner_b200.so"
+OBJ = CSRC / "_obj"
+SOURCES = ["mas_api.cu", "neg_cent.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _deps(src: Path) -> list[Path]:
+    return [src] + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "aligner_b200.h"]
+
+
+def _stale(out: Path, deps: list[Path]) -> bool:
+    return (not out.exists()) or any(d.exists() and d.stat().st_mtime > out.stat().st_mtime for d in deps)
+
+
+def _compile(src: Path, verbose: bool) -> Path:
+    obj = OBJ / (src.stem + ".o")
+    cmd = [NVCC, *FLAGS, "-c", str(src), "-o", str(obj)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src.name, proc.stdout, proc.stderr))
+    if verbose:
+        sys.stderr.write(proc.stderr)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+    OBJ.mkdir(exist_ok=True)
+    todo = [s for s in srcs if force or _stale(OBJ / (s.stem + ".o"), _deps(s))]
+    if todo:
+        with ThreadPoolExecutor(max_workers=len(todo)) as ex:
+            list(ex.map(lambda s: _compile(s, verbose), todo))
+    objs = [OBJ / (s.stem + ".o") for s in srcs]
+    if force or todo or _stale(LIB, objs):
+        cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (proc.stdout, proc.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    out = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(out)

@@ -1,0 +1,366 @@
+// mas_api.cu -- C ABI (include/aligner_b200.h) over the sm_100a MAS kernel.
+//
+// Host side of the boundary that replaces the reference's
+//   maximum_path_c(paths, values, t_xs, t_ys, max_neg_val)   monotonic_align/core.pyx:40
+// There is no CPU fallback in this file: without an sm_100 device every entry
+// point returns ALB200_E_NO_DEVICE.
+#include "mas_kernel.cuh"
+#include "../../include/aligner_b200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+
+namespace alb {
+
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+static thread_local uint64_t g_h2d = 0, g_d2h = 0;
+
+static int fail(int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0, long long d = 0)
+{
+    snprintf(g_err, sizeof(g_err), fmt, a, b, c, d);
+    return code;
+}
+#define ALB_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            snprintf(g_err, sizeof(g_err), "%s failed: %s", #call, cudaGetErrorString(e_));  \
+            return ALB200_E_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+struct DevInfo { int ok, dev, sms, smem_optin, cc_major; };
+
+static int device_info(DevInfo* out)
+{
+    static thread_local DevInfo cache[16];
+    static thread_local bool have[16] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(ALB200_E_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    if (dev < 16 && have[dev]) { *out = cache[dev]; return 0; }
+    DevInfo d; d.dev = dev; d.ok = 1;
+    ALB_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    ALB_CUDA(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    ALB_CUDA(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (d.cc_major != 10)
+        return fail(ALB200_E_NO_DEVICE, "device is sm_%s%lld0, this library is sm_100a only (no fallback)", "", d.cc_major);
+    if (dev < 16) { cache[dev] = d; have[dev] = true; }
+    *out = d;
+    return 0;
+}
+
+// ------------------------------------------------------------------ kernel table
+typedef void (*KernelFn)(const MasParams);
+struct KEntry { int R, TF; KernelFn fn; };
+#define ALB_K(R, TF) { R, TF, mas_kernel<R, TF> }
+static const KEntry g_kernels[] = {
+    ALB_K(1, 32), ALB_K(1, 16), ALB_K(1, 8),
+    ALB_K(2, 32), ALB_K(2, 16), ALB_K(2, 8),
+    ALB_K(3, 32), ALB_K(3, 16), ALB_K(3, 8),
+    ALB_K(4, 32), ALB_K(4, 16), ALB_K(4, 8),
+    ALB_K(6, 32), ALB_K(6, 16), ALB_K(6, 8),
+    ALB_K(8, 32), ALB_K(8, 16), ALB_K(8, 8),
+};
+static KernelFn find_kernel(int R, int TF)
+{
+    for (const KEntry& k : g_kernels)
+        if (k.R == R && k.TF == TF) return k.fn;
+    return nullptr;
+}
+
+struct Config {
+    int R, TF, NW, NS, bits_smem, grid;
+    uint32_t smem;
+    int64_t bits_slot_words;
+    KernelFn fn;
+};
+
+// Picks rows-per-lane, tile width, ring depth and where the direction bits live.
+//   latency regime   (b <= #SM): one CTA per SM, <= 4 warps when possible (one per
+//                    scheduler), deep ring, bits in shared memory.
+//   throughput regime (b > #SM): two CTAs per SM so one item's backtrack overlaps
+//                    another item's streaming.
+static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur, Config* c)
+{
+    int R, NW;
+    if (tx <= 32) { R = 1; NW = 1; }
+    else if (tx <= 1024) {
+        int raw = (tx + 127) / 128;
+        if (raw < 2) raw = 2;
+        R = raw <= 4 ? raw : (raw <= 6 ? 6 : 8);
+        NW = (tx + 32 * R - 1) / (32 * R);
+    } else {
+        R = 8; NW = (tx + 255) / 256;
+    }
+    int f_tf = 0, f_ns = 0, f_bits = -1;
+    if (const char* f = getenv("ALB200_FORCE")) {   // "R,TF,NS,bits_smem" -- tuning / tests only
+        int fr = 0;
+        if (sscanf(f, "%d,%d,%d,%d", &fr, &f_tf, &f_ns, &f_bits) >= 1 && fr > 0) {
+            R = fr; NW = (tx + 32 * R - 1) / (32 * R);
+        }
+    }
+    if (NW > kMaxWarps)
+        return fail(ALB200_E_UNSUPPORTED, "t_x=%s%lld needs more than 16 warps at R=%lld", "", tx, R);
+    const int nblk = (ty + 31) / 32;
+    const int per_sm = di.smem_optin + 1024;                   // 228 KB on sm_100
+    const bool latency = b <= di.sms;
+    const int budgets[2] = { latency ? di.smem_optin : per_sm / 2 - 1024, di.smem_optin };
+    const int tfs[3] = { 32, 16, 8 };
+    int best_tf = 0, best_ns = 0, best_bits = 0;
+    for (int pass = 0; pass < 2 && !best_tf; ++pass) {         // pass 0: want >= 3 stages, pass 1: accept 2
+        for (int bi = 0; bi < 2 && !best_tf; ++bi) {
+            if (bi == 1 && budgets[1] == budgets[0]) break;
+            for (int ti = 0; ti < 3 && !best_tf; ++ti) {
+                if (f_tf && tfs[ti] != f_tf) continue;
+                for (int bs = 1; bs >= 0 && !best_tf; --bs) {
+                    if (f_bits >= 0 && bs != f_bits) continue;
+                    SmemLayout L0 = make_layout(NW, 0, R, tfs[ti], bs, nblk, want_dur);
+                    const int64_t fixed = (int64_t)L0.total + NW * 8 * 8;      // + up to 8 barriers per warp
+                    const int64_t ring = (int64_t)NW * L0.stage_bytes;
+                    int64_t ns = (budgets[bi] - fixed) / ring;
+                    const int cap = latency ? 8 : 4;
+                    if (ns > cap) ns = cap;
+                    if (f_ns) { if (ns < f_ns) continue; ns = f_ns; }
+                    if (ns >= (pass == 0 ? 3 : 2)) { best_tf = tfs[ti]; best_ns = (int)ns; best_bits = bs; }
+                }
+            }
+        }
+    }
+    if (!best_tf)
+        return fail(ALB200_E_UNSUPPORTED, "t_x=%s%lld does not fit the shared-memory ring (max about 3300)", "", tx);
+    c->R = R; c->TF = best_tf; c->NW = NW; c->NS = best_ns; c->bits_smem = best_bits;
+    c->fn = find_kernel(R, best_tf);
+    if (!c->fn) return fail(ALB200_E_UNSUPPORTED, "no kernel instance for R=%s%lld TF=%lld", "", R, best_tf);
+    SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur);
+    c->smem = L.total;
+    c->bits_slot_words = (int64_t)nblk * NW * 32 * R;
+    ALB_CUDA(cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    int occ = 0;
+    ALB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->fn, NW * 32, c->smem));
+    if (occ < 1) return fail(ALB200_E_UNSUPPORTED, "kernel does not fit on an SM (smem %s%lld bytes)", "", c->smem);
+    if (!latency && occ > 4) occ = 4;
+    int64_t g = (int64_t)di.sms * occ;
+    c->grid = (int)(b < g ? b : g);
+    return 0;
+}
+
+static size_t ws_bytes_for(const Config& c)
+{
+    return sizeof(WsHeader) + (c.bits_smem ? 0 : (size_t)c.grid * c.bits_slot_words * 4);
+}
+
+static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t_ys, const void* mask, int mask_dtype,
+                      int64_t msb, int64_t msx, int64_t msy, void* paths, int esize, uint64_t one, int zero_fill,
+                      int32_t* frame_tok, int32_t* durations, int32_t* lens_out, int b, int tx, int ty, float neg,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream)
+{
+    if (!values || b < 0 || tx <= 0 || ty <= 0) return fail(ALB200_E_INVALID, "null values or non-positive shape%s", "");
+    if (!mask && (!t_xs || !t_ys)) return fail(ALB200_E_INVALID, "need lengths or a mask%s", "");
+    if (paths && esize != 1 && esize != 2 && esize != 4 && esize != 8)
+        return fail(ALB200_E_INVALID, "path element size %s%lld not in {1,2,4,8}", "", esize);
+    if (mask && (mask_dtype < 0 || mask_dtype > ALB200_I64)) return fail(ALB200_E_INVALID, "unknown mask dtype %s%lld", "", mask_dtype);
+    if (!workspace) return fail(ALB200_E_INVALID, "null workspace%s", "");
+    if (b == 0) return 0;
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    Config c;
+    rc = select_config(di, b, tx, ty, durations != nullptr, &c);
+    if (rc) return rc;
+    if (workspace_bytes < ws_bytes_for(c))
+        return fail(ALB200_E_INVALID, "workspace too small: %s%lld < %lld bytes", "", (long long)workspace_bytes, (long long)ws_bytes_for(c));
+    MasParams p;
+    memset(&p, 0, sizeof(p));
+    p.values = values; p.paths = paths; p.t_xs = t_xs; p.t_ys = t_ys;
+    p.mask = mask; p.msb = msb; p.msx = msx; p.msy = msy; p.mask_dtype = mask_dtype;
+    p.frame_tok = frame_tok; p.durations = durations; p.lens_out = lens_out;
+    p.ws = reinterpret_cast<WsHeader*>(workspace);
+    p.bits_ws = c.bits_smem ? nullptr : reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(workspace) + sizeof(WsHeader));
+    p.one = one; p.bits_slot_words = c.bits_slot_words;
+    p.B = b; p.Tx = tx; p.Ty = ty; p.esize = esize; p.zero_fill = zero_fill;
+    p.ns = c.NS; p.nblk = (ty + 31) / 32;
+    p.aligned = ((reinterpret_cast<uintptr_t>(values) & 15) == 0 && (ty & 3) == 0) ? 1 : 0;
+    if (getenv("ALB200_FORCE_UNALIGNED")) p.aligned = 0;
+    p.neg = neg;
+    void* args[] = { &p };
+    ALB_CUDA(cudaLaunchKernel((const void*)c.fn, dim3(c.grid), dim3(c.NW * 32), args, c.smem, stream));
+    ++g_launches;
+    return 0;
+}
+
+// ------------------------------------------------------------------ host-pointer path
+struct HostCtx {
+    bool init = false;
+    int dev = -1;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev[32];
+    cudaEvent_t ev_lens = nullptr;
+    float* d_values = nullptr;   size_t cap_values = 0;
+    int32_t* d_ftok = nullptr;   size_t cap_ftok = 0;
+    int32_t* d_lens = nullptr;   size_t cap_lens = 0;
+    void* d_ws[2] = {nullptr, nullptr}; size_t cap_ws = 0;
+    int32_t* h_ftok = nullptr;   size_t cap_hftok = 0;
+    int32_t* h_lens = nullptr;   size_t cap_hlens = 0;
+};
+static thread_local HostCtx g_ctx;
+
+template <typename T>
+static int grow_dev(T** ptr, size_t* cap, size_t need)
+{
+    if (*cap >= need) return 0;
+    if (*ptr) ALB_CUDA(cudaFree(*ptr));
+    *ptr = nullptr; *cap = 0;
+    ALB_CUDA(cudaMalloc(reinterpret_cast<void**>(ptr), need));
+    *cap = need;
+    return 0;
+}
+template <typename T>
+static int grow_host(T** ptr, size_t* cap, size_t need)
+{
+    if (*cap >= need) return 0;
+    if (*ptr) ALB_CUDA(cudaFreeHost(*ptr));
+    *ptr = nullptr; *cap = 0;
+    ALB_CUDA(cudaMallocHost(reinterpret_cast<void**>(ptr), need));
+    *cap = need;
+    return 0;
+}
+
+}  // namespace alb
+
+using namespace alb;
+
+extern "C" {
+
+const char* alb200_last_error(void) { return g_err; }
+const char* alb200_version(void) { return "aligner_b200 0.1.0 sm_100a"; }
+uint64_t alb200_launch_count(void) { return g_launches; }
+void alb200_last_transfer_bytes(uint64_t* h2d, uint64_t* d2h) { if (h2d) *h2d = g_h2d; if (d2h) *d2h = g_d2h; }
+
+int alb200_mas_device(const float* values, const int32_t* t_xs, const int32_t* t_ys, void* paths, int path_elem_size,
+                      uint64_t path_one, int zero_fill, int32_t* frame_tok, int32_t* durations, int b, int tx, int ty,
+                      float max_neg_val, void* workspace, size_t workspace_bytes, void* stream)
+{
+    return launch_mas(values, t_xs, t_ys, nullptr, 0, 0, 0, 0, paths, path_elem_size, path_one, zero_fill, frame_tok,
+                      durations, nullptr, b, tx, ty, max_neg_val, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int alb200_mas_device_masked(const float* values, const void* mask, int mask_dtype, int64_t msb, int64_t msx, int64_t msy,
+                             void* paths, int path_elem_size, uint64_t path_one, int zero_fill, int32_t* frame_tok,
+                             int32_t* durations, int32_t* lens_out, int b, int tx, int ty, float max_neg_val,
+                             void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (!mask) return fail(ALB200_E_INVALID, "null mask%s", "");
+    return launch_mas(values, nullptr, nullptr, mask, mask_dtype, msb, msx, msy, paths, path_elem_size, path_one, zero_fill,
+                      frame_tok, durations, lens_out, b, tx, ty, max_neg_val, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t alb200_mas_workspace_bytes(int b, int tx, int ty)
+{
+    DevInfo di;
+    if (b <= 0 || tx <= 0 || ty <= 0 || device_info(&di)) return sizeof(WsHeader);
+    size_t need = sizeof(WsHeader);
+    for (int dur = 0; dur < 2; ++dur) {
+        Config c;
+        if (select_config(di, b, tx, ty, dur != 0, &c) == 0) need = std::max(need, ws_bytes_for(c));
+    }
+    return need;
+}
+
+int alb200_mas_status(void* workspace, void* stream)
+{
+    if (!workspace) return fail(ALB200_E_INVALID, "null workspace%s", "");
+    int st = 0;
+    WsHeader* h = reinterpret_cast<WsHeader*>(workspace);
+    ALB_CUDA(cudaMemcpyAsync(&st, &h->status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    ALB_CUDA(cudaMemsetAsync(&h->status, 0, sizeof(int), (cudaStream_t)stream));
+    ALB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return st;
+}
+
+int alb200_maximum_path_c(int32_t* paths, const float* values, const int32_t* t_xs, const int32_t* t_ys, int b, int tx,
+                          int ty, float max_neg_val)
+{
+    if (!paths || !values || !t_xs || !t_ys || b < 0 || tx <= 0 || ty <= 0)
+        return fail(ALB200_E_INVALID, "null pointer or non-positive shape%s", "");
+    g_h2d = g_d2h = 0;
+    if (b == 0) return 0;
+    for (int i = 0; i < b; ++i) {
+        const int a = t_xs[i], c = t_ys[i];
+        if (a > 0 && c > 0 && (a > c || a > tx || c > ty))
+            return fail(ALB200_E_LENGTHS, "item %s%lld has t_x=%lld, t_y=%lld (need t_x <= t_y, inside the tensor)", "", i, a, c);
+    }
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    HostCtx& X = g_ctx;
+    if (X.init && X.dev != di.dev) return fail(ALB200_E_INVALID, "host context was created on another device%s", "");
+    if (!X.init) {
+        for (int s = 0; s < 2; ++s) ALB_CUDA(cudaStreamCreateWithFlags(&X.st[s], cudaStreamNonBlocking));
+        for (int i = 0; i < 32; ++i) ALB_CUDA(cudaEventCreateWithFlags(&X.ev[i], cudaEventDisableTiming));
+        ALB_CUDA(cudaEventCreateWithFlags(&X.ev_lens, cudaEventDisableTiming));
+        X.dev = di.dev; X.init = true;
+    }
+    const size_t item_bytes = (size_t)tx * ty * 4;
+    // chunks of about 8 MB so copies, kernels and the host scatter overlap
+    int nch = (int)std::min<size_t>((size_t)b, std::max<size_t>(1, (item_bytes * b) / (8u << 20)));
+    nch = std::min(nch, 32);
+    const int per = (b + nch - 1) / nch;
+    nch = (b + per - 1) / per;
+
+    if ((rc = grow_dev(&X.d_values, &X.cap_values, item_bytes * b))) return rc;
+    if ((rc = grow_dev(&X.d_ftok, &X.cap_ftok, (size_t)b * ty * 4))) return rc;
+    if ((rc = grow_dev(&X.d_lens, &X.cap_lens, (size_t)b * 8))) return rc;
+    if ((rc = grow_host(&X.h_ftok, &X.cap_hftok, (size_t)b * ty * 4))) return rc;
+    if ((rc = grow_host(&X.h_lens, &X.cap_hlens, (size_t)b * 8))) return rc;
+    const size_t wsz = alb200_mas_workspace_bytes(per, tx, ty);
+    if (X.cap_ws < wsz) {
+        for (int s = 0; s < 2; ++s) {
+            if (X.d_ws[s]) ALB_CUDA(cudaFree(X.d_ws[s]));
+            X.d_ws[s] = nullptr;
+            ALB_CUDA(cudaMalloc(&X.d_ws[s], wsz));
+            ALB_CUDA(cudaMemset(X.d_ws[s], 0, wsz));
+        }
+        X.cap_ws = wsz;
+    }
+    memcpy(X.h_lens, t_xs, (size_t)b * 4);
+    memcpy(X.h_lens + b, t_ys, (size_t)b * 4);
+    ALB_CUDA(cudaMemcpyAsync(X.d_lens, X.h_lens, (size_t)b * 8, cudaMemcpyHostToDevice, X.st[0]));
+    ALB_CUDA(cudaEventRecord(X.ev_lens, X.st[0]));
+    ALB_CUDA(cudaStreamWaitEvent(X.st[1], X.ev_lens, 0));
+    g_h2d += (uint64_t)b * 8;
+
+    for (int c = 0; c < nch; ++c) {
+        const int b0 = c * per, nb = std::min(per, b - b0);
+        cudaStream_t s = X.st[c & 1];
+        int mx = 0;
+        for (int i = b0; i < b0 + nb; ++i) if (t_xs[i] > 0 && t_ys[i] > 0) mx = std::max(mx, t_xs[i]);
+        if (mx > 0) {   // rows past the longest item of the chunk are never read: do not ship them
+            ALB_CUDA(cudaMemcpy2DAsync(X.d_values + (size_t)b0 * tx * ty, item_bytes, values + (size_t)b0 * tx * ty, item_bytes,
+                                       (size_t)mx * ty * 4, nb, cudaMemcpyHostToDevice, s));
+            g_h2d += (uint64_t)mx * ty * 4 * nb;
+        }
+        rc = launch_mas(X.d_values + (size_t)b0 * tx * ty, X.d_lens + b0, X.d_lens + b + b0, nullptr, 0, 0, 0, 0, nullptr, 4, 1, 0,
+                        X.d_ftok + (size_t)b0 * ty, nullptr, nullptr, nb, tx, ty, max_neg_val, X.d_ws[c & 1], X.cap_ws, s);
+        if (rc) return rc;
+        ALB_CUDA(cudaMemcpyAsync(X.h_ftok + (size_t)b0 * ty, X.d_ftok + (size_t)b0 * ty, (size_t)nb * ty * 4, cudaMemcpyDeviceToHost, s));
+        g_d2h += (uint64_t)nb * ty * 4;
+        ALB_CUDA(cudaEventRecord(X.ev[c], s));
+    }
+    for (int c = 0; c < nch; ++c) {
+        const int b0 = c * per, nb = std::min(per, b - b0);
+        ALB_CUDA(cudaEventSynchronize(X.ev[c]));
+        for (int i = b0; i < b0 + nb; ++i) {                     // path[index, y] = 1   (core.pyx:33)
+            const int n = (t_xs[i] > 0 && t_ys[i] > 0) ? t_ys[i] : 0;
+            const int32_t* ft = X.h_ftok + (size_t)i * ty;
+            int32_t* pi = paths + (size_t)i * tx * ty;
+            for (int y = 0; y < n; ++y) pi[(size_t)ft[y] * ty + y] = 1;
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+"""Drop-in for the reference package ``monotonic_align`` (monotonic_align/__init__.py:1-21).
+
+``maximum_path(value, mask)`` keeps the reference's signature, return shape,
+dtype rule (``torch.result_type(value, mask)``), device rule (``value.device``)
+and values (exactly 0 / 1), but never leaves the GPU: lengths are derived from
+the mask inside the kernel, the search runs in one sm_100a kernel launch on
+torch's current stream, and the dense path is written directly in the result
+dtype.  PyTorch is only used for device memory and the stream handle.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib
+from .monotonic_align.core import maximum_path_c  # noqa: F401  (same import the reference does, __init__.py:3)
+
+__all__ = ["maximum_path", "maximum_path_lengths", "maximum_path_c", "check_status"]
+
+# bit pattern of 1 in every dtype torch.result_type can produce here
+_ONE = {
+    torch.float32: (4, 0x3F800000), torch.float16: (2, 0x3C00), torch.bfloat16: (2, 0x3F80),
+    torch.float64: (8, 0x3FF0000000000000), torch.int8: (1, 1), torch.uint8: (1, 1), torch.bool: (1, 1),
+    torch.int16: (2, 1), torch.int32: (4, 1), torch.int64: (8, 1),
+}
+_MASK_DTYPE = {
+    torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.float64: _lib.F64,
+    torch.uint8: _lib.U8, torch.bool: _lib.U8, torch.int8: _lib.I8, torch.int16: _lib.I16,
+    torch.int32: _lib.I32, torch.int64: _lib.I64,
+}
+
+_workspaces: dict = {}
+
+
+def _workspace(device: torch.device, stream: int, b: int, tx: int, ty: int) -> torch.Tensor:
+    """Zero-initialised scratch, one per (device, stream) so concurrent launches on
+    different streams never share the work-stealing counter."""
+    need = int(_lib.lib.alb200_mas_workspace_bytes(b, tx, ty))
+    key = (device.index, stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _prep_value(value: torch.Tensor) -> torch.Tensor:
+    if value.dim() != 3:
+        raise ValueError("value must be [b, t_x, t_y], got %s" % (tuple(value.shape),))
+    if not value.is_cuda:
+        raise RuntimeError("aligner_b200 runs on sm_100a only: value must be a CUDA tensor (no CPU fallback)")
+    v = value.detach()
+    if v.dtype != torch.float32:
+        v = v.to(torch.float32)      # what .astype(np.float32) does in the reference (__init__.py:14)
+    return v.contiguous()
+
+
+def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, return_durations: bool = False):
+    """Monotonic alignment search.  Reference: monotonic_align/__init__.py:6-21.
+
+    value: [b, t_x, t_y] scores (log-likelihoods), any float dtype, on a B200.
+    mask:  [b, t_x, t_y] outer product of the text and mel prefix masks, any dtype.
+    Returns the 0/1 path [b, t_x, t_y] in ``torch.result_type(value, mask)`` on
+    ``value.device``; inputs are not modified; no autograd history.
+
+    Differences from the reference, all supersets: bf16 and non-contiguous inputs
+    are accepted; ``return_durations=True`` also returns ``path.sum(-1)`` as int32.
+    The mask must be prefix-shaped (ones in [0,t_x) x [0,t_y), zeros elsewhere),
+    which is what every caller of the reference builds; only mask[:, :, 0] and
+    mask[:, 0, :] are read.
+    """
+    if mask.shape != value.shape:
+        raise ValueError("mask shape %s != value shape %s" % (tuple(mask.shape), tuple(value.shape)))
+    if mask.device != value.device:
+        raise ValueError("mask and value must be on the same device")
+    dtype = torch.result_type(value, mask)
+    if dtype not in _ONE or mask.dtype not in _MASK_DTYPE:
+        raise TypeError("unsupported dtype combination %s / %s" % (value.dtype, mask.dtype))
+    v = _prep_value(value)
+    b, tx, ty = v.shape
+    esize, one = _ONE[dtype]
+    with torch.cuda.device(v.device):
+        path = torch.empty((b, tx, ty), dtype=dtype, device=v.device)
+        dur = torch.empty((b, tx), dtype=torch.int32, device=v.device) if return_durations else None
+        if b == 0 or tx == 0 or ty == 0:
+            return (path.zero_(), dur) if return_durations else path.zero_()
+        stream = torch.cuda.current_stream(v.device).cuda_stream
+        ws = _workspace(v.device, stream, b, tx, ty)
+        m = mask.detach()
+        sb, sx, sy = m.stride()
+        _lib.check(_lib.lib.alb200_mas_device_masked(
+            v.data_ptr(), m.data_ptr(), _MASK_DTYPE[m.dtype], sb, sx, sy,
+            path.data_ptr(), esize, one, 1, None, dur.data_ptr() if dur is not None else None, None,
+            b, tx, ty, -1e9, ws.data_ptr(), ws.numel(), stream))
+    return (path, dur) if return_durations else path
+
+
+def maximum_path_lengths(value: torch.Tensor, x_lengths: torch.Tensor, y_lengths: torch.Tensor, *,
+                         out_dtype: torch.dtype | None = None, dense: bool = True,
+                         return_durations: bool = False, return_frame_tokens: bool = False,
+                         max_neg_val: float = -1e9):
+    """Mask-free entry: lengths given directly as int32 [b] CUDA tensors.
+    Returns a dict with any of 'path', 'durations' (int32 [b,t_x]), 'frame_tokens' (int32 [b,t_y], -1 past t_y)."""
+    v = _prep_value(value)
+    b, tx, ty = v.shape
+    dtype = out_dtype or value.dtype
+    if dtype not in _ONE:
+        raise TypeError("unsupported output dtype %s" % dtype)
+    esize, one = _ONE[dtype]
+    with torch.cuda.device(v.device):
+        xl = x_lengths.to(device=v.device, dtype=torch.int32).contiguous()
+        yl = y_lengths.to(device=v.device, dtype=torch.int32).contiguous()
+        out = {}
+        path = torch.empty((b, tx, ty), dtype=dtype, device=v.device) if dense else None
+        dur = torch.empty((b, tx), dtype=torch.int32, device=v.device) if return_durations else None
+        ftok = torch.empty((b, ty), dtype=torch.int32, device=v.device) if return_frame_tokens else None
+        if b > 0 and tx > 0 and ty > 0:
+            stream = torch.cuda.current_stream(v.device).cuda_stream
+            ws = _workspace(v.device, stream, b, tx, ty)
+            _lib.check(_lib.lib.alb200_mas_device(
+                v.data_ptr(), xl.data_ptr(), yl.data_ptr(),
+                path.data_ptr() if dense else None, esize, one, 1,
+                ftok.data_ptr() if ftok is not None else None, dur.data_ptr() if dur is not None else None,
+                b, tx, ty, max_neg_val, ws.data_ptr(), ws.numel(), stream))
+        if dense:
+            out["path"] = path
+        if dur is not None:
+            out["durations"] = dur
+        if ftok is not None:
+            out["frame_tokens"] = ftok
+    return out
+
+
+def check_status(device=None) -> int:
+    """Synchronises and returns (then clears) the kernel status word for the current
+    stream of `device`: bit 0 = some item had t_x > t_y or lengths outside the tensor
+    (the reference reads out of bounds there; this implementation emits a zero path)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    ws = _workspaces.get((device.index, stream))
+    if ws is None:
+        return 0
+    with torch.cuda.device(device):
+        rc = int(_lib.lib.alb200_mas_status(ws.data_ptr(), stream))
+    if rc < 0:
+        _lib.check(rc)
+    return rc

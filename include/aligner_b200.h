@@ -1,0 +1,130 @@
+/*
+ * aligner_b200.h -- C ABI of libaligner_b200.so (sm_100a only, no CPU fallback).
+ *
+ * This is the drop-in boundary for the one hot path of xiaozhah/Aligner:
+ * monotonic alignment search behind monotonic_align.maximum_path, plus the
+ * score matrices that feed it.  Plain pointers and sizes; no torch, numpy or
+ * Python types.  Every function returns 0 on success or a negative
+ * ALB200_E_* code and never throws; alb200_last_error() describes the last
+ * failure on the calling thread.
+ *
+ * "Reference" citations are relative to the root of xiaozhah/Aligner.
+ */
+#ifndef ALIGNER_B200_H_
+#define ALIGNER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALB200_OK              0
+#define ALB200_E_INVALID      -1   /* bad argument (null pointer, non-positive size, unknown dtype) */
+#define ALB200_E_UNSUPPORTED  -2   /* shape outside what the kernels cover (t_x > 8192) */
+#define ALB200_E_CUDA         -3   /* a CUDA runtime call failed; see alb200_last_error() */
+#define ALB200_E_LENGTHS      -4   /* an item has t_x > t_y, or lengths outside the tensor */
+#define ALB200_E_NO_DEVICE    -5   /* no sm_100 device: this library has no fallback */
+
+/* element types of a mask tensor (alb200_mas_device_masked) */
+#define ALB200_F32  0
+#define ALB200_F16  1
+#define ALB200_BF16 2
+#define ALB200_F64  3
+#define ALB200_U8   4   /* also torch.bool */
+#define ALB200_I8   5
+#define ALB200_I16  6
+#define ALB200_I32  7
+#define ALB200_I64  8
+
+const char *alb200_last_error(void);
+/* "aligner_b200 <version> sm_100a" */
+const char *alb200_version(void);
+
+/* ------------------------------------------------------------------------
+ * Monotonic alignment search, device pointers, asynchronous on `stream`.
+ *
+ * Replaces the body of  maximum_path_c(paths, values, t_xs, t_ys, max_neg_val)
+ * (reference monotonic_align/core.pyx:38-45, per-item work core.pyx:7-35)
+ * for buffers that already live in HBM.
+ *
+ *  values     const float [b, tx, ty], C-contiguous, NOT modified (the reference
+ *             overwrites it with cumulative scores; nothing downstream reads them).
+ *  t_xs,t_ys  const int32 [b] on the device (token / frame counts per item).
+ *  paths      [b, tx, ty] of `path_elem_size`-byte elements, or NULL.  A cell on
+ *             the path receives the bit pattern `path_one` (e.g. 0x3f800000 for
+ *             fp32 1.0, 1 for int32).  If zero_fill != 0 the kernel also writes
+ *             every other cell to zero (fused with the forward pass); with
+ *             zero_fill == 0 the caller has pre-zeroed it, exactly like the
+ *             reference contract (monotonic_align/__init__.py:15).
+ *  frame_tok  optional int32 [b, ty]: token index of every frame, -1 past t_y.
+ *  durations  optional int32 [b, tx]: frames per token (= path.sum(-1)).
+ *  workspace  device scratch of at least alb200_mas_workspace_bytes() bytes that
+ *             was ZERO when first handed to this library and is not touched by
+ *             anyone else afterwards (it holds a self-resetting work counter,
+ *             the status word and spilled direction bits).
+ *  stream     cudaStream_t (NULL = legacy default stream).
+ *
+ * Items with t_x <= 0 or t_y <= 0 produce an all-zero path.  Items with
+ * t_x > t_y (reference: out-of-bounds reads) produce an all-zero
+ * path and set bit 0 of the status word, readable with alb200_mas_status().
+ * ------------------------------------------------------------------------ */
+int alb200_mas_device(const float *values, const int32_t *t_xs, const int32_t *t_ys,
+                      void *paths, int path_elem_size, uint64_t path_one, int zero_fill,
+                      int32_t *frame_tok, int32_t *durations,
+                      int b, int tx, int ty, float max_neg_val,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same, with the lengths derived inside the kernel from a [b,tx,ty] mask the way
+ * the reference's Python layer does (monotonic_align/__init__.py:18-19):
+ *   t_x = sum_x mask[b, x, 0],  t_y = sum_y mask[b, 0, y], truncated to int32.
+ * Strides are in ELEMENTS, so expanded / broadcast masks work.  Only those two
+ * slices of the mask are read: the kernel relies on the mask being the outer
+ * product of two prefix masks, for which `value * mask` (__init__.py:11) is
+ * the identity on every cell the search can read.
+ * lens_out: optional int32 [2, b] receiving (t_x, t_y). */
+int alb200_mas_device_masked(const float *values, const void *mask, int mask_dtype,
+                             int64_t mask_stride_b, int64_t mask_stride_x, int64_t mask_stride_y,
+                             void *paths, int path_elem_size, uint64_t path_one, int zero_fill,
+                             int32_t *frame_tok, int32_t *durations, int32_t *lens_out,
+                             int b, int tx, int ty, float max_neg_val,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
+/* Scratch size for a [b, tx, ty] problem on the current device. */
+size_t alb200_mas_workspace_bytes(int b, int tx, int ty);
+
+/* Synchronises `stream` and returns the status word accumulated in `workspace`
+ * since the last call (then clears it): bit 0 = some item had t_x > t_y or
+ * lengths outside [0,tx]x[0,ty].  Negative = ALB200_E_CUDA. */
+int alb200_mas_status(void *workspace, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Host-pointer entry with the reference's exact calling convention:
+ *   maximum_path_c(paths, values, t_xs, t_ys, max_neg_val=-1e9)
+ * (reference monotonic_align/core.pyx:40; called from __init__.py:20).
+ *
+ *  paths   int32 [b,tx,ty] in HOST memory, pre-zeroed by the caller; ones are
+ *          written in place (core.pyx:33).
+ *  values  const float [b,tx,ty] in HOST memory (pinned memory makes the copy
+ *          asynchronous); NOT clobbered.
+ * Blocking.  Values are staged to the device in chunks on internal streams, the
+ * search runs on the GPU, only the per-frame token indices come back, and the
+ * ones are scattered into `paths` on the host.  Returns ALB200_E_LENGTHS if an
+ * item has t_x > t_y or lengths outside the tensor (checked on the host before
+ * any work).
+ * ------------------------------------------------------------------------ */
+int alb200_maximum_path_c(int32_t *paths, const float *values, const int32_t *t_xs,
+                          const int32_t *t_ys, int b, int tx, int ty, float max_neg_val);
+
+/* Bytes moved by the last alb200_maximum_path_c call on this thread
+ * (host->device, device->host); used by bench.py's e2e accounting. */
+void alb200_last_transfer_bytes(uint64_t *h2d, uint64_t *d2h);
+
+/* Number of kernels this library has launched on this thread since load. */
+uint64_t alb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALIGNER_B200_H_ */

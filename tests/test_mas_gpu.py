@@ -1,0 +1,233 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+
+Reference behaviour under test: monotonic_align/__init__.py:6-21 and core.pyx:7-45.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_values, prefix_mask_np, random_lengths
+from oracle import mas as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ma():
+    import aligner_b200.monotonic_align as m
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return m
+
+
+def oracle_paths(values, t_x, t_y):
+    p = np.zeros(values.shape, np.int32)
+    oracle.maximum_path_c_port(p, values.copy(), np.ascontiguousarray(t_x, np.int32), np.ascontiguousarray(t_y, np.int32), omp=True)
+    return p
+
+
+def gpu_paths(ma, values, t_x, t_y, **kw):
+    v = torch.from_numpy(values).cuda()
+    out = ma.maximum_path_lengths(v, torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda(), out_dtype=torch.int32,
+                                  return_durations=True, return_frame_tokens=True, **kw)
+    torch.cuda.synchronize()
+    return out["path"].cpu().numpy(), out["durations"].cpu().numpy(), out["frame_tokens"].cpu().numpy()
+
+
+def check_against_oracle(ma, values, t_x, t_y):
+    want = oracle_paths(values, t_x, t_y)
+    got, dur, ftok = gpu_paths(ma, values, t_x, t_y)
+    bad = np.argwhere((got != want).reshape(len(t_x), -1).any(1)).ravel()
+    assert bad.size == 0, "items differ: %s (t_x=%s t_y=%s)" % (bad[:8], t_x[bad[:8]], t_y[bad[:8]])
+    assert (dur == want.sum(-1)).all()
+    for i in range(len(t_x)):
+        n = t_y[i] if (t_x[i] > 0 and t_y[i] >= t_x[i]) else 0
+        assert (ftok[i, n:] == -1).all()
+        if n:
+            assert (ftok[i, :n] == want[i].argmax(0)[:n]).all()
+
+
+# ------------------------------------------------------------------ golden + known answers
+def test_golden_vectors_through_public_api(ma, golden):
+    for name, c in golden.items():
+        value, mask = torch.from_numpy(c["value"]).cuda(), torch.from_numpy(c["mask"]).cuda()
+        v0 = value.clone()
+        got = ma.maximum_path(value, mask)
+        assert str(got.dtype) == str(c["path_dtype"]), name
+        assert got.device == value.device and got.shape == value.shape
+        assert not got.requires_grad
+        assert torch.equal(value, v0), "input mutated: " + name
+        assert np.array_equal(got.cpu().numpy(), c["path"]), name
+
+
+# ------------------------------------------------------------------ differential, small shapes, every kernel shape
+FORCES = [None, "1,32,2,1", "1,8,3,0", "2,16,2,1", "2,32,4,0", "3,32,3,1", "4,8,2,1", "6,16,2,0", "8,32,2,1"]
+
+
+@pytest.mark.parametrize("force", FORCES)
+@pytest.mark.parametrize("kind", ["gauss", "ties", "sentinel", "negative"])
+def test_differential_small(ma, monkeypatch, force, kind):
+    if force:
+        monkeypatch.setenv("ALB200_FORCE", force)
+    rng = np.random.default_rng(abs(hash((force, kind))) % (2 ** 31))
+    for trial in range(6):
+        b = int(rng.integers(1, 9))
+        tx = int(rng.integers(1, 300))
+        ty = int(rng.integers(tx, 520))
+        if trial % 2 == 0:
+            ty = (ty + 3) // 4 * 4          # bulk-copy (aligned) path; odd trials take the unaligned loader
+        values = make_values(rng, kind, (b, tx, ty))
+        t_x, t_y = random_lengths(rng, b, tx, ty, full=(trial == 0))
+        check_against_oracle(ma, values, t_x, t_y)
+
+
+def test_unaligned_loader_forced(ma, monkeypatch):
+    monkeypatch.setenv("ALB200_FORCE_UNALIGNED", "1")
+    rng = np.random.default_rng(77)
+    values = make_values(rng, "gauss", (5, 150, 400))
+    t_x, t_y = random_lengths(rng, 5, 150, 400)
+    check_against_oracle(ma, values, t_x, t_y)
+
+
+# ------------------------------------------------------------------ BASELINE.json configs, full size
+@pytest.mark.parametrize("b,tx,ty", [(16, 100, 800), (64, 200, 1000), (32, 300, 1500), (8, 1000, 6000)])
+@pytest.mark.parametrize("kind", ["gauss", "ties"])
+def test_baseline_configs_bit_exact(ma, b, tx, ty, kind):
+    rng = np.random.default_rng(1234 + tx)
+    values = make_values(rng, kind, (b, tx, ty))
+    t_x, t_y = random_lengths(rng, b, tx, ty, full=True)
+    check_against_oracle(ma, values, t_x, t_y)
+
+
+def test_ragged_batch_work_stealing(ma):
+    """More items than resident CTAs, mixed lengths (config 5 in miniature)."""
+    rng = np.random.default_rng(99)
+    b, tx, ty = 1500, 96, 256
+    values = make_values(rng, "gauss", (b, tx, ty))
+    t_x, t_y = random_lengths(rng, b, tx, ty)
+    t_x[::50] = 0                       # sprinkle empty items
+    check_against_oracle(ma, values, t_x, t_y)
+    check_against_oracle(ma, values, t_x, t_y)   # second launch: the work counter re-armed itself
+
+
+def test_config5_shape_properties(ma):
+    """Mixed-length batch at the sweep's shape: invariants that need no oracle, plus a sampled oracle check."""
+    g = torch.Generator(device="cuda").manual_seed(1239)
+    b, tx, ty = 512, 400, 2000
+    rng = np.random.default_rng(1239)
+    t_x = rng.integers(50, tx + 1, b).astype(np.int32)
+    t_y = np.array([rng.integers(max(200, t_x[i]), ty + 1) for i in range(b)], np.int32)
+    values = torch.randn(b, tx, ty, generator=g, device="cuda")
+    out = ma.maximum_path_lengths(values, torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda(), out_dtype=torch.float32,
+                                  return_durations=True, return_frame_tokens=True)
+    path, dur, ftok = out["path"], out["durations"], out["frame_tokens"]
+    txc, tyc = torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda()
+    assert ((path == 0) | (path == 1)).all()
+    assert (path.sum(1).sum(1).int() == tyc).all()                       # exactly one token per real frame
+    ys = torch.arange(ty, device="cuda")[None]
+    assert (path.sum(1)[ys >= tyc[:, None]] == 0).all()                  # nothing past t_y
+    assert (dur == path.sum(-1).int()).all() and (dur.sum(1) == tyc).all()
+    assert (dur[torch.arange(tx, device="cuda")[None] >= txc[:, None]] == 0).all()
+    inb = ys < tyc[:, None]
+    assert (ftok[:, 0] == 0).all()
+    assert (ftok.gather(1, (tyc - 1).long()[:, None])[:, 0] == txc - 1).all()   # ends on the last token
+    step = ftok[:, 1:] - ftok[:, :-1]
+    assert ((step == 0) | (step == 1))[inb[:, 1:]].all()                  # monotone, no skips
+    idx = rng.choice(b, 24, replace=False)
+    want = oracle_paths(values[idx].cpu().numpy(), t_x[idx], t_y[idx])
+    assert np.array_equal(path[idx].cpu().numpy().astype(np.int32), want)
+
+
+# ------------------------------------------------------------------ API behaviour
+@pytest.mark.parametrize("vdt,mdt", [(torch.float32, torch.float32), (torch.float16, torch.float32), (torch.float64, torch.float32),
+                                     (torch.float32, torch.bool), (torch.float32, torch.int64), (torch.float32, torch.float64),
+                                     (torch.bfloat16, torch.bfloat16), (torch.float16, torch.float16), (torch.float32, torch.uint8)])
+def test_api_dtypes(ma, vdt, mdt):
+    rng = np.random.default_rng(31)
+    b, tx, ty = 4, 45, 130
+    t_x, t_y = random_lengths(rng, b, tx, ty)
+    value = torch.from_numpy(make_values(rng, "gauss", (b, tx, ty))).to(vdt)
+    mask = torch.from_numpy(prefix_mask_np(t_x, t_y, tx, ty)).to(mdt)
+    got = ma.maximum_path(value.cuda(), mask.cuda())
+    assert got.dtype == torch.result_type(value, mask)
+    if vdt == torch.bfloat16:       # the reference raises TypeError at .numpy() for bf16; we accept it (exact promotion)
+        want = oracle.maximum_path_port(value.float(), mask.float()).to(got.dtype)
+    else:
+        want = oracle.maximum_path_port(value, mask)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_api_noncontiguous_and_expanded(ma):
+    rng = np.random.default_rng(32)
+    b, tx, ty = 3, 40, 96
+    t_x, t_y = random_lengths(rng, b, tx, ty)
+    base = torch.from_numpy(make_values(rng, "gauss", (b, ty, tx))).cuda()
+    value = base.transpose(1, 2)                                         # non-contiguous view [b,tx,ty]
+    xm = (torch.arange(tx)[None] < torch.from_numpy(t_x)[:, None]).float().cuda()
+    ym = (torch.arange(ty)[None] < torch.from_numpy(t_y)[:, None]).float().cuda()
+    mask = xm[:, :, None].expand(b, tx, ty) * ym[:, None, :].expand(b, tx, ty)
+    got = ma.maximum_path(value, mask)
+    want = oracle_paths(value.contiguous().cpu().numpy(), t_x, t_y)
+    assert np.array_equal(got.cpu().numpy().astype(np.int32), want)
+    # a stride-0 (expanded, never materialised) mask works too
+    full = torch.ones(1, 1, 1, device="cuda").expand(b, tx, ty)
+    got = ma.maximum_path(value, full)
+    want = oracle_paths(value.contiguous().cpu().numpy(), np.full(b, tx, np.int32), np.full(b, ty, np.int32))
+    assert np.array_equal(got.cpu().numpy().astype(np.int32), want)
+
+
+def test_api_edge_shapes(ma):
+    assert ma.maximum_path(torch.zeros(0, 5, 9).cuda(), torch.zeros(0, 5, 9).cuda()).shape == (0, 5, 9)
+    v = torch.randn(2, 1, 1).cuda()
+    assert torch.equal(ma.maximum_path(v, torch.ones_like(v)), torch.ones_like(v))
+    with pytest.raises(RuntimeError):
+        ma.maximum_path(torch.zeros(1, 2, 3), torch.ones(1, 2, 3))        # CPU tensors: no fallback
+    with pytest.raises(ValueError):
+        ma.maximum_path(torch.zeros(1, 2, 3).cuda(), torch.ones(1, 2, 4).cuda())
+
+
+def test_invalid_lengths_flagged_not_crashing(ma):
+    rng = np.random.default_rng(33)
+    values = make_values(rng, "gauss", (3, 20, 30))
+    t_x = np.array([20, 10, 5], np.int32)
+    t_y = np.array([30, 4, 25], np.int32)                                 # item 1 has t_x > t_y
+    ma.check_status()
+    got, dur, ftok = gpu_paths(ma, values, t_x, t_y)
+    assert ma.check_status() == 1 and ma.check_status() == 0
+    assert got[1].sum() == 0 and (ftok[1] == -1).all()
+    want = oracle_paths(values, np.array([20, 0, 5], np.int32), np.array([30, 0, 25], np.int32))
+    assert np.array_equal(got, want)
+
+
+def test_max_neg_val_keyword(ma):
+    rng = np.random.default_rng(34)
+    values = make_values(rng, "negative", (4, 30, 64)) * 10
+    t_x, t_y = random_lengths(rng, 4, 30, 64)
+    for neg in (-1e9, -100.0):
+        want = np.zeros(values.shape, np.int32)
+        oracle.maximum_path_c_port(want, values.copy(), t_x, t_y, max_neg_val=neg)
+        got, _, _ = gpu_paths(ma, values, t_x, t_y, max_neg_val=neg)
+        assert np.array_equal(got, want), neg
+
+
+# ------------------------------------------------------------------ host-pointer entry = the reference's maximum_path_c
+def test_host_maximum_path_c(ma):
+    from monotonic_align.monotonic_align.core import maximum_path_c
+    rng = np.random.default_rng(35)
+    for (b, tx, ty) in [(1, 1, 1), (7, 50, 200), (64, 200, 1000), (40, 97, 333)]:
+        values = make_values(rng, "gauss", (b, tx, ty))
+        t_x, t_y = random_lengths(rng, b, tx, ty)
+        if b > 3:
+            t_x[2] = 0
+        v0 = values.copy()
+        paths = np.zeros(values.shape, np.int32)
+        assert maximum_path_c(paths, values, t_x, t_y) is None
+        assert np.array_equal(values, v0)
+        assert np.array_equal(paths, oracle_paths(values, t_x, t_y))
+    with pytest.raises(ValueError):
+        maximum_path_c(np.zeros((1, 2, 3), np.int64), np.zeros((1, 2, 3), np.float32), np.zeros(1, np.int32), np.zeros(1, np.int32))
+    with pytest.raises(ValueError):
+        maximum_path_c(np.zeros((1, 4, 3), np.int32), np.zeros((1, 4, 3), np.float32), np.array([4], np.int32), np.array([3], np.int32))
+    # keyword form, like core.c:19803 allows
+    paths = np.zeros((1, 2, 3), np.int32)
+    maximum_path_c(paths=paths, values=np.zeros((1, 2, 3), np.float32), t_xs=np.array([2], np.int32), t_ys=np.array([3], np.int32), max_neg_val=-1e9)
+    assert paths.sum() == 3
