@@ -20,7 +20,7 @@ F32, F16, BF16, F64, U8, I8, I16, I32, I64 = range(9)
 # every symbol include/aligner_b200.h declares (tests check the export list against the header)
 SYMBOLS = (
     "alb200_last_error", "alb200_version", "alb200_mas_device", "alb200_mas_device_masked",
-    "alb200_mas_workspace_bytes", "alb200_mas_status", "alb200_maximum_path_c",
+    "alb200_mas_workspace_bytes", "alb200_mas_status", "alb200_mas_describe", "alb200_maximum_path_c",
     "alb200_last_transfer_bytes", "alb200_launch_count",
 )
 
@@ -34,7 +34,7 @@ class AlignerB200Error(RuntimeError):
 def _load() -> ctypes.CDLL:
     if not LIB_PATH.exists():
         raise ImportError(
-            "%s not found: build it with `python -m aligner_b200.build` "
+            "%s not found: build it with `python build_lib.py` "
             "(aligner_b200 has no CPU fallback)" % LIB_PATH)
     lib = ctypes.CDLL(str(LIB_PATH))
     vp, i32, i64, u64, f32, sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64,
@@ -51,6 +51,8 @@ def _load() -> ctypes.CDLL:
     lib.alb200_mas_device_masked.restype = i32
     lib.alb200_mas_workspace_bytes.argtypes = [i32, i32, i32]
     lib.alb200_mas_workspace_bytes.restype = sz
+    lib.alb200_mas_describe.argtypes = [i32, i32, i32, i32, ctypes.c_char_p, sz]
+    lib.alb200_mas_describe.restype = i32
     lib.alb200_mas_status.argtypes = [vp, vp]
     lib.alb200_mas_status.restype = i32
     lib.alb200_maximum_path_c.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32]
@@ -71,6 +73,12 @@ lib = _load()
 def check(rc: int) -> None:
     if rc != OK:
         raise AlignerB200Error(rc, lib.alb200_last_error().decode("utf-8", "replace"))
+
+
+def describe(b: int, tx: int, ty: int, want_durations: bool = False) -> str:
+    buf = ctypes.create_string_buffer(256)
+    check(lib.alb200_mas_describe(b, tx, ty, int(want_durations), buf, 256))
+    return buf.value.decode()
 
 
 def launch_count() -> int:

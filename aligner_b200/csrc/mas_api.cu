@@ -73,7 +73,7 @@ static KernelFn find_kernel(int R, int TF)
 }
 
 struct Config {
-    int R, TF, NW, NS, bits_smem, grid;
+    int R, TF, NW, NS, bits_smem, grid, occ;
     uint32_t smem;
     int64_t bits_slot_words;
     KernelFn fn;
@@ -84,7 +84,7 @@ struct Config {
 //                    scheduler), deep ring, bits in shared memory.
 //   throughput regime (b > #SM): two CTAs per SM so one item's backtrack overlaps
 //                    another item's streaming.
-static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur, Config* c)
+static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool want_dur, Config* c)
 {
     int R, NW;
     if (tx <= 32) { R = 1; NW = 1; }
@@ -138,12 +138,38 @@ static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur
     SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur);
     c->smem = L.total;
     c->bits_slot_words = (int64_t)nblk * NW * 32 * R;
-    ALB_CUDA(cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    ALB_CUDA(cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));   // once per instance, never lowered
     int occ = 0;
     ALB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->fn, NW * 32, c->smem));
     if (occ < 1) return fail(ALB200_E_UNSUPPORTED, "kernel does not fit on an SM (smem %s%lld bytes)", "", c->smem);
     if (!latency && occ > 4) occ = 4;
-    int64_t g = (int64_t)di.sms * occ;
+    c->occ = occ;
+    return 0;
+}
+
+// select_config_uncached costs a few driver calls; remember the answers (per thread, tiny table).
+struct CfgKey { int dev, latency, tx, ty, dur; char env[48]; };
+static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur, Config* c)
+{
+    static thread_local CfgKey keys[8];
+    static thread_local Config vals[8];
+    static thread_local int used = 0, next = 0;
+    CfgKey k;
+    memset(&k, 0, sizeof(k));
+    k.dev = di.dev; k.latency = b <= di.sms; k.tx = tx; k.ty = ty; k.dur = want_dur;
+    if (const char* f = getenv("ALB200_FORCE")) strncpy(k.env, f, sizeof(k.env) - 1);
+    int hit = -1;
+    for (int i = 0; i < used; ++i)
+        if (memcmp(&keys[i], &k, sizeof(k)) == 0) { hit = i; break; }
+    if (hit < 0) {
+        Config fresh;
+        int rc = select_config_uncached(di, b, tx, ty, want_dur, &fresh);
+        if (rc) return rc;
+        hit = next; next = (next + 1) % 8; if (used < 8) ++used;
+        keys[hit] = k; vals[hit] = fresh;
+    }
+    *c = vals[hit];
+    int64_t g = (int64_t)di.sms * c->occ;
     c->grid = (int)(b < g ? b : g);
     return 0;
 }
@@ -268,6 +294,20 @@ size_t alb200_mas_workspace_bytes(int b, int tx, int ty)
         if (select_config(di, b, tx, ty, dur != 0, &c) == 0) need = std::max(need, ws_bytes_for(c));
     }
     return need;
+}
+
+int alb200_mas_describe(int b, int tx, int ty, int want_durations, char* buf, size_t buf_bytes)
+{
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    Config c;
+    rc = select_config(di, b, tx, ty, want_durations != 0, &c);
+    if (rc) return rc;
+    if (buf && buf_bytes)
+        snprintf(buf, buf_bytes, "rows_per_lane=%d tile_frames=%d warps=%d stages=%d bits=%s smem=%u grid=%d ctas_per_sm=%d",
+                 c.R, c.TF, c.NW, c.NS, c.bits_smem ? "smem" : "global", c.smem, c.grid, c.occ);
+    return 0;
 }
 
 int alb200_mas_status(void* workspace, void* stream)

@@ -1,6 +1,8 @@
 """Build libaligner_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m aligner_b200.build [--force] [--verbose]
+    python build_lib.py [--force] [--verbose]
+
+Lives outside the package on purpose: importing aligner_b200 needs the library to exist.
 
 The shared library is the product's only compute path; nothing here builds or
 links the CPU oracle.
@@ -13,7 +15,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
-PKG = Path(__file__).resolve().parent
+PKG = Path(__file__).resolve().parent / "aligner_b200"
 CSRC = PKG / "csrc"
 LIB = PKG / "libaligner_b200.so"
 OBJ = CSRC / "_obj"

@@ -94,6 +94,10 @@ int alb200_mas_device_masked(const float *values, const void *mask, int mask_dty
 /* Scratch size for a [b, tx, ty] problem on the current device. */
 size_t alb200_mas_workspace_bytes(int b, int tx, int ty);
 
+/* Writes a one-line description of the kernel configuration chosen for a
+ * [b, tx, ty] problem (rows per lane, tile width, ring depth, grid) into buf. */
+int alb200_mas_describe(int b, int tx, int ty, int want_durations, char *buf, size_t buf_bytes);
+
 /* Synchronises `stream` and returns the status word accumulated in `workspace`
  * since the last call (then clears it): bit 0 = some item had t_x > t_y or
  * lengths outside [0,tx]x[0,ty].  Negative = ALB200_E_CUDA. */

@@ -14,8 +14,8 @@ ROOT = Path(__file__).resolve().parent.parent
 
 @pytest.fixture(scope="module")
 def lib_path():
-    from aligner_b200 import build
-    return build.build()
+    import build_lib
+    return build_lib.build()
 
 
 def _declared():

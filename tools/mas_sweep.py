@@ -1,0 +1,97 @@
+"""tools/mas_sweep.py -- GPU-side tuning sweep: kernel time of the MAS launch for several
+workloads and forced kernel shapes (ALB200_FORCE="R,TF,NS,bits_smem").  Prints a table and
+writes gpurun_out/sweep.json.  Not part of the product or the tests."""
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import aligner_b200.monotonic_align as ma  # noqa: E402
+from aligner_b200 import _lib  # noqa: E402
+
+PEAK = 6549.1
+
+
+def bench(b, tx, ty, force, ragged=False, reps=30, dense=True):
+    if force:
+        os.environ["ALB200_FORCE"] = force
+    else:
+        os.environ.pop("ALB200_FORCE", None)
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(5)
+    if ragged:
+        t_x = rng.integers(50, tx + 1, b).astype(np.int32)
+        t_y = np.array([rng.integers(max(200, t_x[i]), ty + 1) for i in range(b)], np.int32)
+    else:
+        t_x, t_y = np.full(b, tx, np.int32), np.full(b, ty, np.int32)
+    cells = float((t_x.astype(np.int64) * t_y).sum())
+    padded = float(b) * tx * ty
+    per_set = padded * 8
+    nsets = int(min(max(2, np.ceil(400e6 / per_set) + 1), 8))
+    g = torch.Generator(device=dev).manual_seed(1)
+    vals = [torch.randn(b, tx, ty, generator=g, device=dev) for _ in range(nsets)]
+    outs = [torch.empty(b, tx, ty, device=dev) for _ in range(nsets)]
+    xl, yl = torch.from_numpy(t_x).to(dev), torch.from_numpy(t_y).to(dev)
+    ws = ma._workspace(dev, torch.cuda.current_stream().cuda_stream, b, tx, ty)
+    stream = torch.cuda.current_stream().cuda_stream
+    try:
+        desc = _lib.describe(b, tx, ty)
+    except Exception as e:
+        return {"error": str(e)}
+
+    def launch(i):
+        _lib.check(_lib.lib.alb200_mas_device(vals[i % nsets].data_ptr(), xl.data_ptr(), yl.data_ptr(),
+                                              outs[i % nsets].data_ptr() if dense else None, 4, 0x3F800000, 1, None, None,
+                                              b, tx, ty, -1e9, ws.data_ptr(), ws.numel(), stream))
+    for i in range(3):
+        launch(i)
+    torch.cuda.synchronize()
+    ev = []
+    for i in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); launch(i); e1.record()
+        ev.append((e0, e1))
+    torch.cuda.synchronize()
+    t = np.array([a.elapsed_time(b_) for a, b_ in ev]) * 1e3   # us
+    med = float(np.median(t))
+    algo = 4 * cells + 4 * padded
+    return {"us_med": med, "us_min": float(t.min()), "cells_per_s": cells / (med * 1e-6), "GBps": algo / (med * 1e-6) / 1e9,
+            "frac": algo / (med * 1e-6) / 1e9 / PEAK, "desc": desc}
+
+
+def main():
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    rows = []
+    plans = {
+        "c1": (16, 100, 800, False, [None, "1,32,4,1", "2,32,4,1", "2,16,4,1", "2,32,2,1", "2,32,8,1", "4,32,4,1"]),
+        "c2": (64, 200, 1000, False, [None, "1,32,4,1", "2,32,2,1", "2,32,3,1", "2,32,4,1", "2,32,6,1", "2,16,4,1", "2,16,8,1", "2,8,8,1",
+                                      "3,32,4,1", "4,32,4,1", "2,32,4,0", "8,32,2,1"]),
+        "c3": (32, 300, 1500, False, [None, "2,32,4,1", "3,32,3,1", "3,16,6,1", "4,32,3,1", "3,32,3,0"]),
+        "c4": (8, 1000, 6000, False, [None, "8,16,2,0", "8,8,4,0", "4,16,2,0", "4,8,3,0", "2,8,2,0", "6,16,2,0"]),
+        "c5a": (1024, 400, 2000, True, [None, "4,32,2,0", "4,16,4,0", "4,16,3,0", "4,8,4,0", "3,16,3,0", "6,16,3,0", "8,16,3,0", "2,16,2,0"]),
+        "c5b": (4096, 200, 1000, False, [None, "2,32,3,1", "2,32,2,1", "2,16,4,1", "2,16,4,0", "4,32,2,1", "4,16,4,1", "4,16,4,0", "8,16,4,0", "8,32,2,0"]),
+    }
+    for name, (b, tx, ty, ragged, forces) in plans.items():
+        if which != "all" and which != name:
+            continue
+        for f in forces:
+            r = bench(b, tx, ty, f, ragged)
+            r.update({"workload": name, "force": f})
+            rows.append(r)
+            if "error" in r:
+                print("%-4s %-12s ERROR %s" % (name, f, r["error"]), flush=True)
+            else:
+                print("%-4s %-12s %9.1f us (min %9.1f)  %6.1f GB/s  frac %.3f  %s" % (name, f, r["us_med"], r["us_min"], r["GBps"], r["frac"], r["desc"]), flush=True)
+        torch.cuda.empty_cache()
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "sweep.json").write_text(json.dumps(rows, indent=1))
+
+
+if __name__ == "__main__":
+    main()
