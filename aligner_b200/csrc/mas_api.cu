@@ -55,8 +55,8 @@ static int device_info(DevInfo* out)
 
 // ------------------------------------------------------------------ kernel table
 typedef void (*KernelFn)(const MasParams);
-struct KEntry { int R, TF; KernelFn fn; };
-#define ALB_K(R, TF) { R, TF, mas_kernel<R, TF> }
+struct KEntry { int R, TF, skew; KernelFn fn; };
+#define ALB_K(R, TF) { R, TF, 0, mas_kernel<R, TF, false> }, { R, TF, 1, mas_kernel<R, TF, true> }
 static const KEntry g_kernels[] = {
     ALB_K(1, 32), ALB_K(1, 16), ALB_K(1, 8),
     ALB_K(2, 32), ALB_K(2, 16), ALB_K(2, 8),
@@ -65,15 +65,15 @@ static const KEntry g_kernels[] = {
     ALB_K(6, 32), ALB_K(6, 16), ALB_K(6, 8),
     ALB_K(8, 32), ALB_K(8, 16), ALB_K(8, 8),
 };
-static KernelFn find_kernel(int R, int TF)
+static KernelFn find_kernel(int R, int TF, int skew)
 {
     for (const KEntry& k : g_kernels)
-        if (k.R == R && k.TF == TF) return k.fn;
+        if (k.R == R && k.TF == TF && k.skew == skew) return k.fn;
     return nullptr;
 }
 
 struct Config {
-    int R, TF, NW, NS, bits_smem, grid, occ;
+    int R, TF, NW, NS, bits_smem, skew, grid, occ;
     uint32_t smem;
     int64_t bits_slot_words;
     KernelFn fn;
@@ -96,10 +96,10 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     } else {
         R = 8; NW = (tx + 255) / 256;
     }
-    int f_tf = 0, f_ns = 0, f_bits = -1;
-    if (const char* f = getenv("ALB200_FORCE")) {   // "R,TF,NS,bits_smem" -- tuning / tests only
+    int f_tf = 0, f_ns = 0, f_bits = -1, f_skew = -1;
+    if (const char* f = getenv("ALB200_FORCE")) {   // "R,TF,NS,bits_smem,skew" -- tuning / tests only
         int fr = 0;
-        if (sscanf(f, "%d,%d,%d,%d", &fr, &f_tf, &f_ns, &f_bits) >= 1 && fr > 0) {
+        if (sscanf(f, "%d,%d,%d,%d,%d", &fr, &f_tf, &f_ns, &f_bits, &f_skew) >= 1 && fr > 0) {
             R = fr; NW = (tx + 32 * R - 1) / (32 * R);
         }
     }
@@ -133,7 +133,10 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     if (!best_tf)
         return fail(ALB200_E_UNSUPPORTED, "t_x=%s%lld does not fit the shared-memory ring (max about 3300)", "", tx);
     c->R = R; c->TF = best_tf; c->NW = NW; c->NS = best_ns; c->bits_smem = best_bits;
-    c->fn = find_kernel(R, best_tf);
+    // latency regime: the lane-skewed (systolic) forward keeps the shuffle off the per-frame chain;
+    // throughput regime: several CTAs per SM already hide it, and the lock-step form has no pipeline fill.
+    c->skew = f_skew >= 0 ? f_skew : (latency ? 1 : 0);
+    c->fn = find_kernel(R, best_tf, c->skew);
     if (!c->fn) return fail(ALB200_E_UNSUPPORTED, "no kernel instance for R=%s%lld TF=%lld", "", R, best_tf);
     SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur);
     c->smem = L.total;
@@ -212,9 +215,29 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
     p.aligned = ((reinterpret_cast<uintptr_t>(values) & 15) == 0 && (ty & 3) == 0) ? 1 : 0;
     if (getenv("ALB200_FORCE_UNALIGNED")) p.aligned = 0;
     p.neg = neg;
+    static long long* d_dbg = nullptr;
+    const bool dbg = getenv("ALB200_DBG") != nullptr;
+    const size_t dbg_n = (size_t)c.grid * (kMaxWarps + 2) * 2;
+    if (dbg) {   // developer aid: per-warp clock64 stamps of the first item of every CTA, printed to stderr
+        if (d_dbg) cudaFree(d_dbg);
+        ALB_CUDA(cudaMalloc(&d_dbg, dbg_n * 8));
+        ALB_CUDA(cudaMemset(d_dbg, 0, dbg_n * 8));
+        p.dbg = d_dbg;
+    }
     void* args[] = { &p };
     ALB_CUDA(cudaLaunchKernel((const void*)c.fn, dim3(c.grid), dim3(c.NW * 32), args, c.smem, stream));
     ++g_launches;
+    if (dbg) {
+        long long* h = (long long*)malloc(dbg_n * 8);
+        ALB_CUDA(cudaMemcpy(h, d_dbg, dbg_n * 8, cudaMemcpyDeviceToHost));
+        for (int cta = 0; cta < c.grid && cta < 2; ++cta) {
+            long long* d = h + (size_t)cta * (kMaxWarps + 2) * 2;
+            fprintf(stderr, "[alb200 dbg] cta %d:", cta);
+            for (int w = 0; w < c.NW; ++w) fprintf(stderr, " w%d fwd %lld (end@%lld)", w, d[w * 2 + 1] - d[w * 2], d[w * 2 + 1] - d[0]);
+            fprintf(stderr, " | backtrack starts @%lld, takes %lld cycles\n", d[kMaxWarps * 2] - d[0], d[kMaxWarps * 2 + 1] - d[kMaxWarps * 2]);
+        }
+        free(h);
+    }
     return 0;
 }
 
@@ -305,8 +328,8 @@ int alb200_mas_describe(int b, int tx, int ty, int want_durations, char* buf, si
     rc = select_config(di, b, tx, ty, want_durations != 0, &c);
     if (rc) return rc;
     if (buf && buf_bytes)
-        snprintf(buf, buf_bytes, "rows_per_lane=%d tile_frames=%d warps=%d stages=%d bits=%s smem=%u grid=%d ctas_per_sm=%d",
-                 c.R, c.TF, c.NW, c.NS, c.bits_smem ? "smem" : "global", c.smem, c.grid, c.occ);
+        snprintf(buf, buf_bytes, "rows_per_lane=%d tile_frames=%d warps=%d stages=%d bits=%s form=%s smem=%u grid=%d ctas_per_sm=%d",
+                 c.R, c.TF, c.NW, c.NS, c.bits_smem ? "smem" : "global", c.skew ? "skewed" : "lockstep", c.smem, c.grid, c.occ);
     return 0;
 }
 

@@ -14,10 +14,13 @@
 // this formulation and is proven equal to the table form by tests/test_oracle.py.
 //
 // Data movement
-//   * every warp streams ITS OWN rows: per-row cp.async.bulk (TMA engine, SASS
-//     UBLKCP) copies of TF frames land in a per-warp ring of NS stages and
-//     complete on a per-stage mbarrier.  Rows are placed with a 16-byte skew per
-//     lane so the lanes' 128-bit shared loads are bank-conflict free for any R.
+//   * every warp streams ITS OWN rows: 128-bit asynchronous copies (cp.async.cg,
+//     SASS LDGSTS.128) of TF frames per row land in a per-warp ring of NS stages
+//     and complete on a per-stage mbarrier (cp.async.mbarrier.arrive).  Rows are
+//     placed with a 16-byte skew per lane so the lanes' 128-bit shared loads are
+//     bank-conflict free for any R.  (Per-row cp.async.bulk copies were measured
+//     first: ~60-90 cycles of TMA issue per 128-byte row made the loader the
+//     bottleneck, 8x slower end to end -- profiles/r01_notes.md.)
 //   * only tiles inside the reference's band (core.pyx:18) are fetched.
 //   * warps are a dataflow pipeline: warp w consumes the last row of warp w-1
 //     through a small shared ring + progress flag, 16 frames at a time.  The
@@ -39,7 +42,7 @@ namespace alb {
 
 constexpr int kMaxWarps = 16;
 constexpr int kRing = 64;          // floats in a warp-boundary ring (4 units of 16 frames)
-constexpr int kZeroChunk = 4096;   // bytes per zero-fill bulk store
+constexpr int kZeroChunk = 8192;   // bytes per zero-fill bulk store
 constexpr int kLanePad = 16;       // bytes of skew per lane inside a tile stage
 constexpr int kProgDone = 0x3fffffff;
 
@@ -62,6 +65,7 @@ struct MasParams {
     int32_t* lens_out;
     WsHeader* ws;
     uint32_t* bits_ws;          // global direction-bit slots (nullptr when bits are in smem)
+    long long* dbg;             // optional [grid][kMaxWarps+2][2] clock64 stamps (ALB200_DBG)
     uint64_t one;
     int64_t bits_slot_words;
     int B, Tx, Ty;
@@ -88,8 +92,8 @@ __host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF,
     L.stage_bytes = RW * TF * 4 + 32 * kLanePad;
     uint32_t o = 0;
     L.off_bar = o;  o += NW * NS * 8;
-    L.off_prog = alb_align(o, 16); o = L.off_prog + (NW + 1) * 4;
-    L.off_misc = alb_align(o, 16); o = L.off_misc + 64;
+    L.off_prog = alb_align(o, 16); o = L.off_prog + (2 * NW + 2) * 4;   // tail (lane 31) and head (lane 0) progress per warp
+    L.off_misc = alb_align(o, 16); o = L.off_misc + 64 + 2 * 16 * 8;     // item/lengths + per-warp partial mask sums
     L.off_bnd = alb_align(o, 16);  o = L.off_bnd + NW * kRing * 4;
     L.off_zero = alb_align(o, 128); o = L.off_zero + kZeroChunk;
     L.off_ring = alb_align(o, 128); o = L.off_ring + NW * NS * L.stage_bytes;
@@ -126,6 +130,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS), L2 only
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// the mbarrier receives one arrival when all of this thread's earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 // shared -> global bulk store
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -145,36 +157,63 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
 __device__ __forceinline__ void sts32(uint32_t a, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v));
 }
-__device__ __forceinline__ int ld_acquire_s32(uint32_t a) {
+// Progress flags between neighbouring warps of one CTA.  Producer: the SAME lane stores the boundary
+// values and then the flag; consumer: reads the flag, then the values.  Shared-memory accesses of one
+// thread are performed in program order by the SM's in-order LSU pipe, so plain volatile accesses are
+// sufficient; ld.acquire/st.release compile to MEMBAR.ALL.CTA, which also drains this thread's in-flight
+// LDGSTS tile loads and cost ~1 us per 16-frame unit (measured, profiles/r01_notes.md).
+__device__ __forceinline__ int ld_flag(uint32_t a) {
     int v;
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_s32(uint32_t a, int v) {
-    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+__device__ __forceinline__ void st_flag(uint32_t a, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
 // ------------------------------------------------------------------ mask -> length
 // reference: t_x = mask.sum(1)[:,0], t_y = mask.sum(2)[:,0], astype(int32)  (__init__.py:18-19)
-__device__ __forceinline__ double mask_elem(const void* m, int dtype, int64_t i) {
-    switch (dtype) {
-        case 0: return (double)((const float*)m)[i];
-        case 1: return (double)__half2float(__ushort_as_half(((const unsigned short*)m)[i]));
-        case 2: return (double)__uint_as_float(((uint32_t)((const unsigned short*)m)[i]) << 16);
-        case 3: return ((const double*)m)[i];
-        case 4: return (double)((const uint8_t*)m)[i];
-        case 5: return (double)((const int8_t*)m)[i];
-        case 6: return (double)((const int16_t*)m)[i];
-        case 7: return (double)((const int32_t*)m)[i];
-        default: return (double)((const long long*)m)[i];
+// Every thread of the CTA takes elements tid, tid+n, ... of the concatenation [mask[b,:,0] ; mask[b,0,:]] with four
+// independent loads in flight (the first version walked them one dependent load at a time: ~15% of the kernel).
+template <typename T> __device__ __forceinline__ double mask_to_double(T v) { return (double)v; }
+template <> __device__ __forceinline__ double mask_to_double<__half>(__half v) { return (double)__half2float(v); }
+struct bf16_raw { unsigned short u; };
+template <> __device__ __forceinline__ double mask_to_double<bf16_raw>(bf16_raw v) { return (double)__uint_as_float(((uint32_t)v.u) << 16); }
+
+template <typename T>
+__device__ __forceinline__ void mask_partial(const void* mv, int64_t base, int64_t sx, int64_t sy, int Tx, int Ty, int tid, int nthr,
+                                             double& ax, double& ay)
+{
+    const T* m = reinterpret_cast<const T*>(mv) + base;
+    const int n = Tx + Ty;
+    for (int i0 = tid; i0 < n; i0 += 4 * nthr) {
+        T v[4];
+        int idx[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            idx[q] = i0 + q * nthr;
+            if (idx[q] < n) v[q] = m[idx[q] < Tx ? (int64_t)idx[q] * sx : (int64_t)(idx[q] - Tx) * sy];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (idx[q] < n) { if (idx[q] < Tx) ax += mask_to_double(v[q]); else ay += mask_to_double(v[q]); }
+        }
     }
 }
-__device__ __forceinline__ int warp_mask_sum(const void* m, int dtype, int64_t base, int64_t stride, int n, int lane) {
-    double s = 0.0;
-    for (int i = lane; i < n; i += 32) s += mask_elem(m, dtype, base + (int64_t)i * stride);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    return (int)s;   // truncation, like astype(np.int32)
+__device__ __forceinline__ void mask_partial_any(const void* m, int dtype, int64_t base, int64_t sx, int64_t sy, int Tx, int Ty,
+                                                 int tid, int nthr, double& ax, double& ay)
+{
+    switch (dtype) {
+        case 0: mask_partial<float>(m, base, sx, sy, Tx, Ty, tid, nthr, ax, ay); break;
+        case 1: mask_partial<__half>(m, base, sx, sy, Tx, Ty, tid, nthr, ax, ay); break;
+        case 2: mask_partial<bf16_raw>(m, base, sx, sy, Tx, Ty, tid, nthr, ax, ay); break;
+        case 3: mask_partial<double>(m, base, sx, sy, Tx, Ty, tid, nthr, ax, ay); break;
+        case 4: mask_partial<uint8_t>(m, base, sx, sy, Tx, Ty, tid, nthr, ax, ay); break;
+        case 5: mask_partial<int8_t>(m, base, sx, sy, Tx, Ty, tid, nthr, ax, ay); break;
+        case 6: mask_partial<int16_t>(m, base, sx, sy, Tx, Ty, tid, nthr, ax, ay); break;
+        case 7: mask_partial<int32_t>(m, base, sx, sy, Tx, Ty, tid, nthr, ax, ay); break;
+        default: mask_partial<long long>(m, base, sx, sy, Tx, Ty, tid, nthr, ax, ay); break;
+    }
 }
 
 __device__ __forceinline__ void store_one(void* paths, int64_t elem, int esize, uint64_t one) {
@@ -233,8 +272,72 @@ __device__ __forceinline__ void mas_unit(float (&old)[R], float& up, uint32_t (&
     }
 }
 
+// ------------------------------------------------------------------ forward unit, lane-skewed (systolic) form
+// Lane l runs 4 frames behind lane l-1: at the same instruction it works on frame (Y - 4*l).  The neighbour's value
+// a lane needs was produced five frames earlier, so the shuffle that fetches it is issued four frames before its use
+// and its latency never sits on the per-frame dependency chain (in the lock-step form above it does, every frame).
+// Cost: 4 frames of pipeline fill per lane.  Tiles are loaded with the same per-lane skew, so in lane-local terms
+// the shared-memory addressing is identical to the lock-step form.
+//   upn[k]   neighbour value for frame k of the NEXT group of four (fetched during this group)
+//   lastp    this lane's last-row value of the previous frame (what the next shuffle ships)
+//   wbits[r] 32-frame direction word being shifted in from the top, 4 bits per group
+template <int R, int TF, int UNIT, bool DIAG>
+__device__ __forceinline__ void mas_unit_skew(float (&old)[R], float (&upn)[4], float& lastp, uint32_t (&wbits)[R],
+                                              uint32_t tile_addr, uint32_t bin_addr, uint32_t bout_addr, int Y, int yl,
+                                              int w, int lane, float neg, int dxy, uint32_t* bits_row, int TXS, int y_lo,
+                                              unsigned span)
+{
+#pragma unroll
+    for (int g = 0; g < UNIT / 4; ++g) {
+        float4 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = lds128(tile_addr + r * (TF * 4) + g * 16);
+        float4 bin;
+        if (w > 0) {
+            bin = lds128(bin_addr + (((Y + 4 * g) & (kRing - 1)) << 2));
+        } else {
+            bin = make_float4(neg, neg, neg, neg);
+            if (Y + 4 * g == 0) bin.x = 0.f;
+        }
+        uint32_t hb[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) hb[r] = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int kk = 4 * g + k;
+            const float bk = (k == 0) ? bin.x : (k == 1) ? bin.y : (k == 2) ? bin.z : bin.w;
+            const float upv = (lane == 0) ? bk : upn[k];
+            float nv[R];
+#pragma unroll
+            for (int r = R - 1; r >= 0; --r) {
+                const float stay = old[r];
+                const float move = (r == 0) ? upv : old[r - 1];
+                const bool take = move > stay;
+                const float vr = (k == 0) ? v[r].x : (k == 1) ? v[r].y : (k == 2) ? v[r].z : v[r].w;
+                float res = (take ? move : stay) + vr;
+                if (DIAG) res = (dxy + r > kk) ? neg : res;
+                nv[r] = res;
+                if (take) hb[r] |= (1u << k);
+            }
+            upn[k] = __shfl_up_sync(0xffffffffu, lastp, 1);     // consumed at frame k of the next group
+            lastp = nv[R - 1];
+            if (lane == 31) sts32(bout_addr + (((yl + kk + 1) & (kRing - 1)) << 2), nv[R - 1]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) old[r] = nv[r];
+        }
+        const int yg = yl + 4 * g;
+#pragma unroll
+        for (int r = 0; r < R; ++r) wbits[r] = __funnelshift_r(wbits[r], hb[r], 4);
+        if ((yg & 31) == 28 && (unsigned)(yg - y_lo) < span) {
+            uint32_t* brow = bits_row + (int64_t)(yg >> 5) * TXS;
+#pragma unroll
+            for (int r = 0; r < R; ++r) brow[r] = wbits[r];
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the kernel
-template <int R, int TF>
+template <int R, int TF, bool SKEW>
 __global__ void __launch_bounds__(kMaxWarps * 32) mas_kernel(const MasParams p)
 {
     constexpr int RW = 32 * R;
@@ -250,7 +353,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32) mas_kernel(const MasParams p)
     const SmemLayout L = make_layout(NW, NS, R, TF, bits_smem, p.nblk, p.durations != nullptr);
 
     const uint32_t bar0 = smem_u32(smem + L.off_bar) + w * NS * 8;
-    const uint32_t prog_a = smem_u32(smem + L.off_prog);            // prog[w] at prog_a + 4*w
+    const uint32_t prog_a = smem_u32(smem + L.off_prog);            // tail progress of warp w at +4*w, head progress at +4*(NW+w)
+    const uint32_t head_a = prog_a + 4 * NW;
+    double* msum = reinterpret_cast<double*>(smem + L.off_misc + 64);   // [w][2] partial mask sums
     int* misc = reinterpret_cast<int*>(smem + L.off_misc);          // [0]=item [1]=t_x [2]=t_y
     const uint32_t bnd_a = smem_u32(smem + L.off_bnd);
     const uint32_t zero_a = smem_u32(smem + L.off_zero);
@@ -261,7 +366,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) mas_kernel(const MasParams p)
 
     // ---- one-time setup
     if (lane == 0)
-        for (int s = 0; s < NS; ++s) mbar_init(bar0 + 8 * s, 1);
+        for (int s = 0; s < NS; ++s) mbar_init(bar0 + 8 * s, 32);      // one arrival per lane
     for (int i = tid; i < kZeroChunk / 16; i += blockDim.x)
         reinterpret_cast<int4*>(smem + L.off_zero)[i] = make_int4(0, 0, 0, 0);
     fence_mbar_init();
@@ -272,26 +377,40 @@ __global__ void __launch_bounds__(kMaxWarps * 32) mas_kernel(const MasParams p)
     const int64_t item_elems = (int64_t)p.Tx * p.Ty;
 
     int item = blockIdx.x;
+    const bool dbg_on = (p.dbg != nullptr);
+    long long* dbg = dbg_on ? p.dbg + (int64_t)blockIdx.x * (kMaxWarps + 2) * 2 : nullptr;
+    bool first_item = true;
     while (item < p.B) {
+        if (dbg_on && first_item && lane == 0) dbg[w * 2] = clock64();
         // ---- lengths
         if (p.mask != nullptr) {
-            if (w == 0) {
-                int tx = warp_mask_sum(p.mask, p.mask_dtype, (int64_t)item * p.msb, p.msx, p.Tx, lane);
-                if (lane == 0) misc[1] = tx;
+            double ax = 0.0, ay = 0.0;
+            mask_partial_any(p.mask, p.mask_dtype, (int64_t)item * p.msb, p.msx, p.msy, p.Tx, p.Ty, tid, blockDim.x, ax, ay);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ax += __shfl_xor_sync(0xffffffffu, ax, o);
+                ay += __shfl_xor_sync(0xffffffffu, ay, o);
             }
-            if (w == (NW > 1 ? 1 : 0)) {
-                int ty = warp_mask_sum(p.mask, p.mask_dtype, (int64_t)item * p.msb, p.msy, p.Ty, lane);
-                if (lane == 0) misc[2] = ty;
-            }
+            if (lane == 0) { msum[2 * w] = ax; msum[2 * w + 1] = ay; }
         } else if (tid == 0) {
             misc[1] = p.t_xs[item];
             misc[2] = p.t_ys[item];
         }
-        if (tid < NW) st_release_s32(prog_a + 4 * tid, tid * RW);
+        if (tid < NW) {
+            st_flag(prog_a + 4 * tid, SKEW ? -(1 << 28) : tid * RW);
+            st_flag(head_a + 4 * tid, tid * RW);
+        }
         if (p.durations != nullptr)
             for (int i = tid; i < TXS; i += blockDim.x) durS[i] = 0;
         __syncthreads();
-        int t_x = misc[1], t_y = misc[2];
+        int t_x, t_y;
+        if (p.mask != nullptr) {          // sum the per-warp partials; truncation like astype(np.int32) (__init__.py:18-19)
+            double ax = 0.0, ay = 0.0;
+            for (int q = 0; q < NW; ++q) { ax += msum[2 * q]; ay += msum[2 * q + 1]; }
+            t_x = (int)ax; t_y = (int)ay;
+        } else {
+            t_x = misc[1]; t_y = misc[2];
+        }
         if (p.lens_out != nullptr && tid == 0) {
             p.lens_out[item] = t_x;
             p.lens_out[p.B + item] = t_y;
@@ -343,31 +462,49 @@ __global__ void __launch_bounds__(kMaxWarps * 32) mas_kernel(const MasParams p)
             const int nrows = x1 - x0;
             const int y_start = x0;                                 // first frame where any of our rows is on/below the diagonal
             const int y_last = t_y - t_x + x1 - 1;                  // last frame where our last row is inside the band (core.pyx:18)
-            int y_end = (y_last + UNIT) / UNIT * UNIT;              // exclusive, whole units
+            // lock-step: whole units up to y_last.  skewed: whole 32-frame words, plus 124 frames so lane 31 finishes too.
+            const int span = SKEW ? ((y_last + 1 - y_start + 31) & ~31) : 0;
+            const int y_end = SKEW ? y_start + span + 128 : (y_last + UNIT) / UNIT * UNIT;
             const int t_s = y_start / TF;
-            const int y_cap = y_end < p.Ty ? y_end : p.Ty;
+            const int y_cap = SKEW ? y_end : (y_end < p.Ty ? y_end : p.Ty);
             const int t_e = (y_cap + TF - 1) / TF;                  // tiles [t_s, t_e)
             const bool has_consumer = (x1 < t_x);
             const float* vrow = p.values + item * item_elems + (int64_t)x0 * p.Ty;
+            const int band_hi0 = t_y - t_x + x0;                    // last live frame of row i is band_hi0 + i
 
+            // One tile = our rows x TF frames (per-lane skewed by 4 frames in SKEW mode).  Loader lane = (16-byte chunk
+            // ck of a row, row group q); it walks the owner lanes li = q, q+RPI, ... and their R rows, so one warp-wide
+            // LDGSTS.128 moves RPI whole row segments: full 32..128-byte global segments, conflict-free shared writes.
+            constexpr int CPR = TF / 4;            // 16-byte chunks per row
+            constexpr int RPI = 32 / CPR;          // row segments per warp instruction
+            const int ck = lane % CPR, q0 = lane / CPR;
             auto issue_tile = [&](int t) {
-                const int f0 = t * TF;
-                const int nf = (p.Ty - f0 < TF) ? p.Ty - f0 : TF;
+                const int f0 = t * TF + ck * 4;
                 const uint32_t bar = bar0 + 8 * pstage;
-                const uint32_t st = ring_a + pstage * L.stage_bytes;
-                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nrows * nf * 4));
-                for (int i = lane; i < nrows; i += 32)
-                    bulk_g2s(st + i * (TF * 4) + (i / R) * kLanePad, vrow + (int64_t)i * p.Ty + f0, (uint32_t)(nf * 4), bar);
+                const uint32_t st = ring_a + pstage * L.stage_bytes + ck * 16;
+                for (int li = q0; li * R < nrows; li += RPI) {
+                    const int f = SKEW ? f0 - 4 * li : f0;                       // frame of this chunk for owner lane li
+                    const int lo = SKEW ? ((x0 + li * R) & ~3) : 0;              // chunks wholly above the diagonal are never read
+                    const uint32_t d = st + li * LANE_STRIDE;
+                    const float* src = vrow + (int64_t)(li * R) * p.Ty + f;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = li * R + r;
+                        const bool in = SKEW ? (f >= lo && f <= band_hi0 + i) : true;
+                        if (i < nrows && in && f + 4 <= p.Ty) cp_async16(d + r * (TF * 4), src + (int64_t)r * p.Ty);
+                    }
+                }
+                cp_async_arrive(bar);
                 if (++pstage == (uint32_t)NS) pstage = 0;
             };
             auto load_tile_sync = [&](int t) {   // unaligned inputs: plain 4-byte loads into stage 0
                 const int f0 = t * TF;
-                const int nf = (p.Ty - f0 < TF) ? p.Ty - f0 : TF;
                 float* st = reinterpret_cast<float*>(smem + L.off_ring + (size_t)w * NS * L.stage_bytes);
                 __syncwarp();
                 for (int idx = lane; idx < nrows * TF; idx += 32) {
-                    const int i = idx / TF, f = idx - i * TF;
-                    if (f < nf) st[(i * (TF * 4) + (i / R) * kLanePad) / 4 + f] = vrow[(int64_t)i * p.Ty + f0 + f];
+                    const int i = idx / TF, fl = idx - i * TF, li = i / R;
+                    const int f = SKEW ? f0 + fl - 4 * li : f0 + fl;
+                    if (f >= 0 && f < p.Ty) st[(i * (TF * 4) + li * kLanePad) / 4 + fl] = vrow[(int64_t)i * p.Ty + f];
                 }
                 __syncwarp();
             };
@@ -385,37 +522,53 @@ __global__ void __launch_bounds__(kMaxWarps * 32) mas_kernel(const MasParams p)
             uint32_t wbits[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) { old[r] = p.neg; wbits[r] = 0u; }
-            float up = p.neg;
+            float up = p.neg;                                       // lock-step form
+            float upn[4] = { p.neg, p.neg, p.neg, p.neg };          // skewed form
+            float lastp = p.neg;
             const int xl0 = x0 + lane * R;
+            const int lag = SKEW ? 4 * lane : 0;
             const uint32_t bin_addr = bnd_a + (w > 0 ? (w - 1) : 0) * kRing * 4;
             const uint32_t bout_addr = bnd_a + w * kRing * 4;
+            const int diag_end = SKEW ? x0 + RW + 124 : x1;
             int seen_cons = 0;
 
-            for (int y = y_start; y < y_end; y += UNIT) {
+            for (int y = y_start; y < y_end; y += UNIT) {           // y = frame of lane 0
                 const int fin = y & (TF - 1);
                 if (fin == 0) {
                     if (p.aligned) mbar_wait(bar0 + 8 * cstage, cphase);
                     else load_tile_sync(y / TF);
                 }
                 if (w > 0) {
-                    while (ld_acquire_s32(prog_a + 4 * (w - 1)) < y + UNIT) { }
+                    while (ld_flag(prog_a + 4 * (w - 1)) < y + UNIT) { }
                 }
                 if (has_consumer) {
-                    const int need = y + UNIT - (kRing - 1);
-                    while (seen_cons < need) seen_cons = ld_acquire_s32(prog_a + 4 * (w + 1));
+                    const int need = y - (SKEW ? 124 : 0) + UNIT - (kRing - 1);   // our lane 31 is about to overwrite these ring slots
+                    while (seen_cons < need) seen_cons = ld_flag(head_a + 4 * (w + 1));
                 }
                 const uint32_t tile_addr = (p.aligned ? ring_a + cstage * L.stage_bytes : ring_a) + lane * LANE_STRIDE + fin * 4;
-                uint32_t hb[R];
+                if constexpr (SKEW) {
+                    const int yl = y - lag;
+                    if (y < diag_end)
+                        mas_unit_skew<R, TF, UNIT, true>(old, upn, lastp, wbits, tile_addr, bin_addr, bout_addr, y, yl, w, lane, p.neg,
+                                                         xl0 - yl, bits + xl0, TXS, y_start, (unsigned)span);
+                    else
+                        mas_unit_skew<R, TF, UNIT, false>(old, upn, lastp, wbits, tile_addr, bin_addr, bout_addr, y, yl, w, lane, p.neg,
+                                                          0, bits + xl0, TXS, y_start, (unsigned)span);
+                    if (lane == 31) st_flag(prog_a + 4 * w, y + UNIT - 124);
+                    if (lane == 0) st_flag(head_a + 4 * w, y + UNIT);
+                } else {
+                    uint32_t hb[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) hb[r] = 0u;
-                if (y < x1)
-                    mas_unit<R, TF, UNIT, true>(old, up, hb, tile_addr, bin_addr, bout_addr, y, w, lane, p.neg, xl0 - y);
-                else
-                    mas_unit<R, TF, UNIT, false>(old, up, hb, tile_addr, bin_addr, bout_addr, y, w, lane, p.neg, 0);
-                const int pos = y & 31;
+                    for (int r = 0; r < R; ++r) hb[r] = 0u;
+                    if (y < diag_end)
+                        mas_unit<R, TF, UNIT, true>(old, up, hb, tile_addr, bin_addr, bout_addr, y, w, lane, p.neg, xl0 - y);
+                    else
+                        mas_unit<R, TF, UNIT, false>(old, up, hb, tile_addr, bin_addr, bout_addr, y, w, lane, p.neg, 0);
+                    const int pos = y & 31;
 #pragma unroll
-                for (int r = 0; r < R; ++r) wbits[r] |= hb[r] << pos;
-                if (lane == 31) st_release_s32(prog_a + 4 * w, y + UNIT);
+                    for (int r = 0; r < R; ++r) wbits[r] |= hb[r] << pos;
+                    if (lane == 31) { st_flag(prog_a + 4 * w, y + UNIT); st_flag(head_a + 4 * w, y + UNIT); }
+                }
 
                 const int yn = y + UNIT;
                 if ((yn & (TF - 1)) == 0 || yn >= y_end) {          // tile consumed
@@ -427,13 +580,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32) mas_kernel(const MasParams p)
                     }
                     if (zf) issue_zero(zq);
                 }
-                if ((yn & 31) == 0 || yn >= y_end) {                // direction word complete
+                if (!SKEW && ((yn & 31) == 0 || yn >= y_end)) {     // direction word complete (lock-step form)
                     uint32_t* brow = bits + (int64_t)(y >> 5) * TXS + xl0;
 #pragma unroll
                     for (int r = 0; r < R; ++r) { brow[r] = wbits[r]; wbits[r] = 0u; }
                 }
             }
-            if (lane == 31) st_release_s32(prog_a + 4 * w, kProgDone);
+            if (lane == 31) st_flag(prog_a + 4 * w, kProgDone);
+            if (dbg_on && first_item && lane == 0) dbg[w * 2 + 1] = clock64();
         }
         if (zf && w < nact) {
             issue_zero(0x7fffffff);
@@ -442,6 +596,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) mas_kernel(const MasParams p)
         __syncthreads();
 
         // ================= backtrack (warp 0) =================
+        if (dbg_on && first_item && tid == 0) dbg[kMaxWarps * 2] = clock64();
         if (w == 0) {
             int tok0 = t_x - 1;
             for (int blk = (t_y - 1) >> 5; blk >= 0; --blk) {
@@ -452,12 +607,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32) mas_kernel(const MasParams p)
                 const int dg = row - yb;                                            // diagonal cell of this row: forced step (index == y)
                 if (row > 0 && dg >= 0 && dg < 32) wd |= (1u << dg);
                 if (nvalid < 32) wd &= (1u << nvalid) - 1u;
+                // transpose the 32x32 bit block with 32 ballots FIRST (independent, pipelined), then walk: the walk's
+                // dependent chain is one AND and one ADD per frame on a one-hot position.
+                uint32_t m[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) m[k] = __ballot_sync(0xffffffffu, (wd & (1u << k)) != 0u);
                 uint32_t pos = 1u, mine = 1u;
 #pragma unroll
                 for (int k = 31; k >= 0; --k) {
-                    const uint32_t m = __ballot_sync(0xffffffffu, (wd >> k) & 1u);
                     if (lane == k) mine = pos;
-                    pos = pos + (pos & m);
+                    pos = pos + (pos & m[k]);
                 }
                 if (lane < nvalid) {
                     const int tok = tok0 - (__ffs(mine) - 1);
@@ -477,6 +636,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) mas_kernel(const MasParams p)
         if (p.durations != nullptr)
             for (int i = tid; i < p.Tx; i += blockDim.x) p.durations[(int64_t)item * p.Tx + i] = (i < t_x) ? durS[i] : 0;
 
+        if (dbg_on && first_item && tid == 0) dbg[kMaxWarps * 2 + 1] = clock64();
+        first_item = false;
         // ---- next item
         if (p.B <= (int)gridDim.x) break;
         if (tid == 0) misc[0] = atomicAdd(&p.ws->counter, 1) + (int)gridDim.x;

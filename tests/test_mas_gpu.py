@@ -60,7 +60,9 @@ def test_golden_vectors_through_public_api(ma, golden):
 
 
 # ------------------------------------------------------------------ differential, small shapes, every kernel shape
-FORCES = [None, "1,32,2,1", "1,8,3,0", "2,16,2,1", "2,32,4,0", "3,32,3,1", "4,8,2,1", "6,16,2,0", "8,32,2,1"]
+# "rows_per_lane,tile_frames,stages,bits_in_smem,skewed" -- every kernel shape in both forward forms
+FORCES = [None, "1,32,2,1,0", "1,8,3,0,1", "2,16,2,1,0", "2,32,4,0,1", "2,32,2,1,1", "3,32,3,1,0", "3,16,3,0,1", "4,8,2,1,1",
+          "4,32,2,1,0", "6,16,2,0,0", "6,32,2,1,1", "8,32,2,1,1", "8,16,2,0,0"]
 
 
 @pytest.mark.parametrize("force", FORCES)
@@ -80,11 +82,22 @@ def test_differential_small(ma, monkeypatch, force, kind):
         check_against_oracle(ma, values, t_x, t_y)
 
 
-def test_unaligned_loader_forced(ma, monkeypatch):
+@pytest.mark.parametrize("skew", ["0", "1"])
+def test_unaligned_loader_forced(ma, monkeypatch, skew):
     monkeypatch.setenv("ALB200_FORCE_UNALIGNED", "1")
+    monkeypatch.setenv("ALB200_FORCE", "2,32,2,1," + skew)
     rng = np.random.default_rng(77)
     values = make_values(rng, "gauss", (5, 150, 400))
     t_x, t_y = random_lengths(rng, 5, 150, 400)
+    check_against_oracle(ma, values, t_x, t_y)
+
+
+@pytest.mark.parametrize("skew", ["0", "1"])
+def test_both_forward_forms_on_ragged_batch(ma, monkeypatch, skew):
+    monkeypatch.setenv("ALB200_FORCE", "2,32,3,1," + skew)
+    rng = np.random.default_rng(78)
+    values = make_values(rng, "ties", (40, 200, 600))
+    t_x, t_y = random_lengths(rng, 40, 200, 600)
     check_against_oracle(ma, values, t_x, t_y)
 
 
