@@ -55,20 +55,27 @@ static int device_info(DevInfo* out)
 
 // ------------------------------------------------------------------ kernel table
 typedef void (*KernelFn)(const MasParams);
-struct KEntry { int R, TF, skew; KernelFn fn; };
-#define ALB_K(R, TF) { R, TF, 0, mas_kernel<R, TF, false> }, { R, TF, 1, mas_kernel<R, TF, true> }
+struct KEntry { int R, TF, skew, nwmax, minb; KernelFn fn; };
+// lock-step form: a 255-register instance for the latency regime and a 128-register one for two CTAs per SM;
+// skewed form: latency regime only.
+#define ALB_K(R, TF) { R, TF, 0, 4, 1, mas_kernel<R, TF, false, 4, 1> }, { R, TF, 0, 4, 2, mas_kernel<R, TF, false, 4, 2> }, \
+                     { R, TF, 1, 4, 1, mas_kernel<R, TF, true, 4, 1> }
+#define ALB_K8(R, TF) { R, TF, 0, 8, 1, mas_kernel<R, TF, false, 8, 1> }, { R, TF, 1, 8, 1, mas_kernel<R, TF, true, 8, 1> }
 static const KEntry g_kernels[] = {
-    ALB_K(1, 32), ALB_K(1, 16), ALB_K(1, 8),
-    ALB_K(2, 32), ALB_K(2, 16), ALB_K(2, 8),
-    ALB_K(3, 32), ALB_K(3, 16), ALB_K(3, 8),
-    ALB_K(4, 32), ALB_K(4, 16), ALB_K(4, 8),
-    ALB_K(6, 32), ALB_K(6, 16), ALB_K(6, 8),
+    ALB_K(1, 32),
+    ALB_K(2, 32), ALB_K(2, 16),
+    ALB_K(3, 32), ALB_K(3, 16),
+    ALB_K(4, 32), ALB_K(4, 16),
+    ALB_K(6, 32), ALB_K(6, 16),
     ALB_K(8, 32), ALB_K(8, 16), ALB_K(8, 8),
+    ALB_K(16, 16), ALB_K(16, 8),
+    ALB_K8(8, 32), ALB_K8(8, 16), ALB_K8(8, 8),      // more than 4 compute warps: t_x > 1024
+    ALB_K8(16, 16), ALB_K8(16, 8),
 };
-static KernelFn find_kernel(int R, int TF, int skew)
+static KernelFn find_kernel(int R, int TF, int skew, int nw, int minb)
 {
     for (const KEntry& k : g_kernels)
-        if (k.R == R && k.TF == TF && k.skew == skew) return k.fn;
+        if (k.R == R && k.TF == TF && k.skew == skew && nw <= k.nwmax && k.minb <= minb) return k.fn;   // minb 1 also serves minb 2 requests
     return nullptr;
 }
 
@@ -93,8 +100,10 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
         if (raw < 2) raw = 2;
         R = raw <= 4 ? raw : (raw <= 6 ? 6 : 8);
         NW = (tx + 32 * R - 1) / (32 * R);
-    } else {
+    } else if (tx <= 2048) {
         R = 8; NW = (tx + 255) / 256;
+    } else {
+        R = 16; NW = (tx + 511) / 512;
     }
     int f_tf = 0, f_ns = 0, f_bits = -1, f_skew = -1;
     if (const char* f = getenv("ALB200_FORCE")) {   // "R,TF,NS,bits_smem,skew" -- tuning / tests only
@@ -103,13 +112,13 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
             R = fr; NW = (tx + 32 * R - 1) / (32 * R);
         }
     }
-    if (NW > kMaxWarps)
-        return fail(ALB200_E_UNSUPPORTED, "t_x=%s%lld needs more than 16 warps at R=%lld", "", tx, R);
+    if (NW > (R >= 8 ? kMaxWarps : 4))
+        return fail(ALB200_E_UNSUPPORTED, "t_x=%s%lld needs too many compute warps at %lld rows per lane", "", tx, R);
     const int nblk = (ty + 31) / 32;
     const int per_sm = di.smem_optin + 1024;                   // 228 KB on sm_100
     const bool latency = b <= di.sms;
     const int budgets[2] = { latency ? di.smem_optin : per_sm / 2 - 1024, di.smem_optin };
-    const int tfs[3] = { 32, 16, 8 };
+    const int tfs[3] = { R >= 16 ? 16 : 32, R == 1 ? 32 : 16, R >= 8 ? 8 : (R == 1 ? 32 : 16) };
     int best_tf = 0, best_ns = 0, best_bits = 0;
     for (int pass = 0; pass < 2 && !best_tf; ++pass) {         // pass 0: want >= 3 stages, pass 1: accept 2
         for (int bi = 0; bi < 2 && !best_tf; ++bi) {
@@ -119,7 +128,7 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
                 for (int bs = 1; bs >= 0 && !best_tf; --bs) {
                     if (f_bits >= 0 && bs != f_bits) continue;
                     SmemLayout L0 = make_layout(NW, 0, R, tfs[ti], bs, nblk, want_dur);
-                    const int64_t fixed = (int64_t)L0.total + NW * 8 * 8;      // + up to 8 barriers per warp
+                    const int64_t fixed = (int64_t)L0.total + 2 * NW * 8 * 8;  // + up to 8 full and 8 empty barriers per warp
                     const int64_t ring = (int64_t)NW * L0.stage_bytes;
                     int64_t ns = (budgets[bi] - fixed) / ring;
                     const int cap = latency ? 8 : 4;
@@ -135,15 +144,21 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     c->R = R; c->TF = best_tf; c->NW = NW; c->NS = best_ns; c->bits_smem = best_bits;
     // latency regime: the lane-skewed (systolic) forward keeps the shuffle off the per-frame chain;
     // throughput regime: several CTAs per SM already hide it, and the lock-step form has no pipeline fill.
-    c->skew = f_skew >= 0 ? f_skew : (latency ? 1 : 0);
-    c->fn = find_kernel(R, best_tf, c->skew);
+    // skewed (systolic) forward: the shuffle leaves the per-frame chain, but every lane adds 4 frames of pipeline fill
+    // and every warp hand-off another 124, so it only pays when one compute warp covers the whole text axis.
+    c->skew = f_skew >= 0 ? f_skew : ((latency && NW == 1) ? 1 : 0);
+    c->fn = nullptr;
+    if (!latency && !c->skew)
+        for (const KEntry& k : g_kernels)
+            if (k.R == R && k.TF == best_tf && k.skew == 0 && NW <= k.nwmax && k.minb == 2) { c->fn = k.fn; break; }
+    if (!c->fn) c->fn = find_kernel(R, best_tf, c->skew, NW, 1);
     if (!c->fn) return fail(ALB200_E_UNSUPPORTED, "no kernel instance for R=%s%lld TF=%lld", "", R, best_tf);
     SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur);
     c->smem = L.total;
     c->bits_slot_words = (int64_t)nblk * NW * 32 * R;
     ALB_CUDA(cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));   // once per instance, never lowered
     int occ = 0;
-    ALB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->fn, NW * 32, c->smem));
+    ALB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->fn, 2 * NW * 32, c->smem));
     if (occ < 1) return fail(ALB200_E_UNSUPPORTED, "kernel does not fit on an SM (smem %s%lld bytes)", "", c->smem);
     if (!latency && occ > 4) occ = 4;
     c->occ = occ;
@@ -211,13 +226,18 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
     p.bits_ws = c.bits_smem ? nullptr : reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(workspace) + sizeof(WsHeader));
     p.one = one; p.bits_slot_words = c.bits_slot_words;
     p.B = b; p.Tx = tx; p.Ty = ty; p.esize = esize; p.zero_fill = zero_fill;
-    p.ns = c.NS; p.nblk = (ty + 31) / 32;
+    p.nw = c.NW; p.ns = c.NS; p.nblk = (ty + 31) / 32;
+    {
+        const SmemLayout L = make_layout(c.NW, c.NS, c.R, c.TF, c.bits_smem, p.nblk, durations != nullptr);
+        p.off_full = L.off_full; p.off_empty = L.off_empty; p.off_flags = L.off_flags; p.off_misc = L.off_misc; p.off_bnd = L.off_bnd;
+        p.off_zero = L.off_zero; p.off_ring = L.off_ring; p.off_bits = L.off_bits; p.off_dur = L.off_dur; p.stage_bytes = L.stage_bytes;
+    }
     p.aligned = ((reinterpret_cast<uintptr_t>(values) & 15) == 0 && (ty & 3) == 0) ? 1 : 0;
     if (getenv("ALB200_FORCE_UNALIGNED")) p.aligned = 0;
     p.neg = neg;
     static long long* d_dbg = nullptr;
     const bool dbg = getenv("ALB200_DBG") != nullptr;
-    const size_t dbg_n = (size_t)c.grid * (kMaxWarps + 2) * 2;
+    const size_t dbg_n = (size_t)c.grid * ((2 * kMaxWarps + 2) * 2 + kMaxWarps * 4);
     if (dbg) {   // developer aid: per-warp clock64 stamps of the first item of every CTA, printed to stderr
         if (d_dbg) cudaFree(d_dbg);
         ALB_CUDA(cudaMalloc(&d_dbg, dbg_n * 8));
@@ -225,16 +245,24 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
         p.dbg = d_dbg;
     }
     void* args[] = { &p };
-    ALB_CUDA(cudaLaunchKernel((const void*)c.fn, dim3(c.grid), dim3(c.NW * 32), args, c.smem, stream));
+    ALB_CUDA(cudaLaunchKernel((const void*)c.fn, dim3(c.grid), dim3(2 * c.NW * 32), args, c.smem, stream));
     ++g_launches;
     if (dbg) {
         long long* h = (long long*)malloc(dbg_n * 8);
         ALB_CUDA(cudaMemcpy(h, d_dbg, dbg_n * 8, cudaMemcpyDeviceToHost));
         for (int cta = 0; cta < c.grid && cta < 2; ++cta) {
-            long long* d = h + (size_t)cta * (kMaxWarps + 2) * 2;
-            fprintf(stderr, "[alb200 dbg] cta %d:", cta);
-            for (int w = 0; w < c.NW; ++w) fprintf(stderr, " w%d fwd %lld (end@%lld)", w, d[w * 2 + 1] - d[w * 2], d[w * 2 + 1] - d[0]);
-            fprintf(stderr, " | backtrack starts @%lld, takes %lld cycles\n", d[kMaxWarps * 2] - d[0], d[kMaxWarps * 2 + 1] - d[kMaxWarps * 2]);
+            long long* d = h + (size_t)cta * (2 * kMaxWarps + 2) * 2;
+            const long long t0 = d[2 * kMaxWarps * 2];
+            fprintf(stderr, "[alb200 dbg] cta %d: lengths %lld |", cta, d[0] - t0);
+            for (int w = 0; w < c.NW; ++w) fprintf(stderr, " w%d fwd %lld (end@%lld)", w, d[w * 2 + 1] - d[w * 2], d[w * 2 + 1] - t0);
+            for (int w = c.NW; w < 2 * c.NW; ++w) fprintf(stderr, " ld%d end@%lld", w - c.NW, d[w * 2 + 1] - t0);
+            fprintf(stderr, " | item done @%lld\n", d[2 * kMaxWarps * 2 + 1] - t0);
+            for (int w = 0; w < c.NW; ++w) {
+                long long* e = h + (size_t)c.grid * (2 * kMaxWarps + 2) * 2 + ((size_t)cta * kMaxWarps + w) * 4;
+                if (e[3] > 0)
+                    fprintf(stderr, "[alb200 dbg]   w%d: %lld units; per unit: wait-full %lld, polls %lld, compute %lld, other %lld cycles\n", w, e[3],
+                            e[0] / e[3], e[1] / e[3], e[2] / e[3], ((d[w * 2 + 1] - d[w * 2]) - e[0] - e[1] - e[2]) / e[3]);
+            }
         }
         free(h);
     }
