@@ -22,6 +22,7 @@ SYMBOLS = (
     "alb200_last_error", "alb200_version", "alb200_mas_device", "alb200_mas_device_masked",
     "alb200_mas_workspace_bytes", "alb200_mas_status", "alb200_mas_describe", "alb200_maximum_path_c",
     "alb200_last_transfer_bytes", "alb200_launch_count",
+    "alb200_neg_cent_gaussian", "alb200_neg_cent_ota",
 )
 
 
@@ -57,13 +58,10 @@ def _load() -> ctypes.CDLL:
     lib.alb200_mas_status.restype = i32
     lib.alb200_maximum_path_c.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32]
     lib.alb200_maximum_path_c.restype = i32
-    if hasattr(lib, "alb200_neg_cent_gaussian"):
-        lib.alb200_neg_cent_gaussian.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
-        lib.alb200_neg_cent_gaussian.restype = i32
-        lib.alb200_neg_cent_ota.argtypes = [vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, i32, vp, sz, vp]
-        lib.alb200_neg_cent_ota.restype = i32
-        lib.alb200_neg_cent_workspace_bytes.argtypes = [i32, i32, i32, i32]
-        lib.alb200_neg_cent_workspace_bytes.restype = sz
+    lib.alb200_neg_cent_gaussian.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.alb200_neg_cent_gaussian.restype = i32
+    lib.alb200_neg_cent_ota.argtypes = [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]
+    lib.alb200_neg_cent_ota.restype = i32
     return lib
 
 

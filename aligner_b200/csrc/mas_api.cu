@@ -14,8 +14,8 @@
 
 namespace alb {
 
-static thread_local char g_err[512] = "";
-static thread_local uint64_t g_launches = 0;
+thread_local char g_err[512] = "";          // also written by neg_cent.cu
+thread_local uint64_t g_launches = 0;
 static thread_local uint64_t g_h2d = 0, g_d2h = 0;
 
 static int fail(int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0, long long d = 0)

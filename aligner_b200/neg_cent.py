@@ -1,0 +1,69 @@
+"""Score matrices that feed ``monotonic_align.maximum_path`` -- CUDA (sm_100a) only.
+
+The reference snapshot has no code for these: the functions mirror the
+upstream expressions users of the reference write in their training step,
+
+    Glow-TTS / VITS:   neg_cent = gaussian_neg_cent(z_p, m_p, logs_p)     # [b, t_text, t_mel]
+                       attn = monotonic_align.maximum_path(neg_cent, attn_mask)
+    OTA / NeMo:        logp = ota_log_prob(queries, keys, prior=attn_prior)
+                       attn_hard = monotonic_align.maximum_path(logp, attn_mask)
+
+PyTorch is used for device memory and the stream handle only.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("aligner_b200 runs on sm_100a only: %s must be a CUDA tensor (no CPU fallback)" % name)
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def gaussian_neg_cent(z: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor) -> torch.Tensor:
+    """z [b,c,t_mel], m_p / logs_p [b,c,t_text]  ->  neg_cent [b,t_text,t_mel] fp32:
+    sum_c log N(z[b,c,y]; m_p[b,c,x], exp(logs_p[b,c,x])^2)  (Glow-TTS logp1..4, VITS neg_cent1..4)."""
+    z, m_p, logs_p = _f32c(z, "z"), _f32c(m_p, "m_p"), _f32c(logs_p, "logs_p")
+    if z.dim() != 3 or m_p.shape != logs_p.shape or m_p.dim() != 3 or z.shape[:2] != m_p.shape[:2]:
+        raise ValueError("expected z [b,c,t_y], m_p [b,c,t_x], logs_p [b,c,t_x]; got %s %s %s" % (tuple(z.shape), tuple(m_p.shape), tuple(logs_p.shape)))
+    b, c, ty = z.shape
+    tx = m_p.shape[2]
+    with torch.cuda.device(z.device):
+        out = torch.empty((b, tx, ty), dtype=torch.float32, device=z.device)
+        if b and tx and ty:
+            _lib.check(_lib.lib.alb200_neg_cent_gaussian(z.data_ptr(), m_p.data_ptr(), logs_p.data_ptr(), out.data_ptr(), b, c, tx, ty,
+                                                         torch.cuda.current_stream(z.device).cuda_stream))
+    return out
+
+
+def ota_log_prob(queries: torch.Tensor, keys: torch.Tensor, temperature: float = 0.0005, prior: torch.Tensor | None = None,
+                 x_lengths: torch.Tensor | None = None) -> torch.Tensor:
+    """queries [b,c,t_mel], keys [b,c,t_text]  ->  [b,t_text,t_mel] fp32:
+    log_softmax over the text axis of -temperature * ||q - k||^2, plus log(prior + 1e-8) if given
+    (OTA aligner, arXiv 2108.10447; NeMo AlignmentEncoder)."""
+    q, k = _f32c(queries, "queries"), _f32c(keys, "keys")
+    if q.dim() != 3 or k.dim() != 3 or q.shape[:2] != k.shape[:2]:
+        raise ValueError("expected queries [b,c,t_y], keys [b,c,t_x]; got %s %s" % (tuple(q.shape), tuple(k.shape)))
+    b, c, ty = q.shape
+    tx = k.shape[2]
+    pr = None
+    if prior is not None:
+        pr = _f32c(prior, "prior")
+        if tuple(pr.shape) != (b, tx, ty):
+            raise ValueError("prior must be [b,t_x,t_y]")
+    xl = None
+    if x_lengths is not None:
+        xl = x_lengths.to(device=q.device, dtype=torch.int32).contiguous()
+    with torch.cuda.device(q.device):
+        out = torch.empty((b, tx, ty), dtype=torch.float32, device=q.device)
+        if b and tx and ty:
+            _lib.check(_lib.lib.alb200_neg_cent_ota(q.data_ptr(), k.data_ptr(), pr.data_ptr() if pr is not None else None,
+                                                    xl.data_ptr() if xl is not None else None, out.data_ptr(), float(temperature),
+                                                    b, c, tx, ty, torch.cuda.current_stream(q.device).cuda_stream))
+    return out

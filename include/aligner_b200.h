@@ -125,6 +125,29 @@ int alb200_maximum_path_c(int32_t *paths, const float *values, const int32_t *t_
  * (host->device, device->host); used by bench.py's e2e accounting. */
 void alb200_last_transfer_bytes(uint64_t *h2d, uint64_t *d2h);
 
+/* ------------------------------------------------------------------------
+ * Score matrices that feed the search (device pointers, asynchronous on `stream`).
+ * The reference snapshot has no code for these (its MoBo/RoMo/OTA branches are not in the
+ * tree, README.md:9-25); they implement the published formulas of the projects it links to
+ * and produce the layout the reference API documents: [b, t_text, t_mel], t_mel contiguous
+ * (monotonic_align/__init__.py:8-9).  fp32 in, fp32 out, fp32 accumulation in a fixed order.
+ *
+ * Gaussian prior (Glow-TTS / VITS `neg_cent1..4`):
+ *   out[b,x,y] = sum_c log N(z[b,c,y]; m_p[b,c,x], exp(logs_p[b,c,x])^2)
+ *   z [b,c,ty], m_p [b,c,tx], logs_p [b,c,tx], out [b,tx,ty].
+ * ------------------------------------------------------------------------ */
+int alb200_neg_cent_gaussian(const float *z, const float *m_p, const float *logs_p, float *out,
+                             int b, int c, int tx, int ty, void *stream);
+
+/* OTA aligner (arXiv 2108.10447, README.md:50; NeMo AlignmentEncoder):
+ *   d[b,x,y]   = -temperature * sum_c (queries[b,c,y] - keys[b,c,x])^2
+ *   out[b,x,y] = log_softmax(d, over x) + log(prior[b,x,y] + 1e-8)
+ * queries [b,c,ty] (mel side), keys [b,c,tx] (text side), prior optional [b,tx,ty],
+ * x_lengths optional int32 [b]: text positions past it are left out of the softmax (-inf). */
+int alb200_neg_cent_ota(const float *queries, const float *keys, const float *prior,
+                        const int32_t *x_lengths, float *out, float temperature,
+                        int b, int c, int tx, int ty, void *stream);
+
 /* Number of kernels this library has launched on this thread since load. */
 uint64_t alb200_launch_count(void);
 

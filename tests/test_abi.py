@@ -45,7 +45,7 @@ def test_product_does_not_import_oracle():
         src = py.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), py
     for cu in (ROOT / "aligner_b200" / "csrc").glob("*.cu*"):
-        assert "oracle/" not in cu.read_text().replace("oracle/mas_oracle.c:mas_oracle_bits", ""), cu
+        assert not re.search(r"#\s*include[^\n]*oracle", cu.read_text()), cu   # comments may cite the oracle, code may not include it
 
 
 def test_sass_uses_bulk_copy_engine(lib_path):

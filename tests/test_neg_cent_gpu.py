@@ -1,0 +1,106 @@
+"""GPU: the score-matrix kernels against the fp64 oracle (oracle/neg_cent.py; parity unpinned, see its header),
+and the north-star agreement criterion: MAS on the kernel's output vs MAS on the oracle's output."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mas as mas_oracle
+from oracle import neg_cent as nc_oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5      # north star: "within 1e-5 relative in fp32"; relative to the max |value| of the item, because
+                # -0.5 z^2 s2 + z m s2 - 0.5 m^2 s2 cancels (neg_cent precision)
+
+
+@pytest.fixture(scope="module")
+def nc():
+    import aligner_b200.neg_cent as m
+    return m
+
+
+def rel_err(got, want):
+    finite = np.isfinite(want)
+    assert (np.isfinite(got) == finite).all()
+    scale = max(np.abs(want[finite]).max(), 1e-30) if finite.any() else 1.0
+    if np.abs(want[finite]).max() == 0.0:
+        return float(np.abs(got[finite]).max())
+    return np.abs(got[finite] - want[finite]).max() / scale
+
+
+@pytest.mark.parametrize("b,c,tx,ty", [(1, 1, 1, 1), (3, 7, 5, 9), (2, 192, 64, 128), (4, 192, 200, 1000), (2, 80, 130, 515), (1, 33, 301, 77)])
+def test_gaussian_matches_fp64(nc, b, c, tx, ty):
+    g = torch.Generator(device="cuda").manual_seed(1234 + tx)
+    z = torch.randn(b, c, ty, generator=g, device="cuda")
+    m = torch.randn(b, c, tx, generator=g, device="cuda")
+    logs = torch.rand(b, c, tx, generator=g, device="cuda") * 1.5 - 1.0          # U(-1, 0.5), SURVEY.md 8d
+    got = nc.gaussian_neg_cent(z, m, logs)
+    assert got.shape == (b, tx, ty) and got.dtype == torch.float32
+    want = nc_oracle.gaussian_neg_cent(z.cpu().numpy(), m.cpu().numpy(), logs.cpu().numpy())
+    assert rel_err(got.cpu().numpy(), want) <= TOL
+    again = nc.gaussian_neg_cent(z, m, logs)
+    assert torch.equal(got, again), "not deterministic"
+
+
+@pytest.mark.parametrize("b,c,tx,ty,with_prior,with_len", [(1, 1, 1, 1, False, False), (3, 80, 37, 150, True, True), (2, 80, 300, 1500, False, False),
+                                                            (2, 80, 300, 333, True, False), (1, 16, 2000, 70, False, True)])
+def test_ota_matches_fp64(nc, b, c, tx, ty, with_prior, with_len):
+    g = torch.Generator(device="cuda").manual_seed(99 + tx)
+    q = torch.randn(b, c, ty, generator=g, device="cuda")
+    k = torch.randn(b, c, tx, generator=g, device="cuda")
+    prior = None
+    if with_prior:
+        prior = torch.rand(b, tx, ty, generator=g, device="cuda")
+    xl = None
+    if with_len:
+        xl = torch.randint(1, tx + 1, (b,), generator=g, device="cuda", dtype=torch.int32)
+    got = nc.ota_log_prob(q, k, 0.0005, prior, xl)
+    want = nc_oracle.ota_log_prob(q.cpu().numpy(), k.cpu().numpy(), 0.0005, None if prior is None else prior.cpu().numpy(),
+                                  None if xl is None else xl.cpu().numpy())
+    assert rel_err(got.cpu().numpy(), want) <= TOL
+    if not with_prior:      # a log-softmax: every frame's column sums to one over the text axis
+        p = torch.exp(got.double()).sum(1)
+        assert torch.allclose(p, torch.ones_like(p), atol=1e-5)
+
+
+def _agreement(ma, score_gpu, score_ref64, t_x, t_y):
+    ref32 = np.ascontiguousarray(score_ref64.astype(np.float32))
+    want = np.zeros(ref32.shape, np.int32)
+    mas_oracle.maximum_path_c_port(want, ref32.copy(), t_x, t_y, omp=True)
+    got = ma.maximum_path_lengths(score_gpu, torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda(), out_dtype=torch.int32)["path"]
+    return float((got.cpu().numpy() == want).mean())
+
+
+def test_paths_agree_gaussian(nc):
+    """North star: paths from the fused score kernel agree with the reference formulation on >= 99.99% of cells."""
+    import aligner_b200.monotonic_align as ma
+    b, c, tx, ty = 16, 192, 200, 1000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    z = torch.randn(b, c, ty, generator=g, device="cuda")
+    m = torch.randn(b, c, tx, generator=g, device="cuda")
+    logs = torch.rand(b, c, tx, generator=g, device="cuda") * 1.5 - 1.0
+    rng = np.random.default_rng(5)
+    t_x = rng.integers(50, tx + 1, b).astype(np.int32)
+    t_y = np.array([rng.integers(max(200, t_x[i]), ty + 1) for i in range(b)], np.int32)
+    score = nc.gaussian_neg_cent(z, m, logs)
+    ref = nc_oracle.gaussian_neg_cent(z.cpu().numpy(), m.cpu().numpy(), logs.cpu().numpy())
+    assert _agreement(ma, score, ref, t_x, t_y) >= 0.9999
+
+
+def test_paths_agree_ota(nc):
+    import aligner_b200.monotonic_align as ma
+    b, c, tx, ty = 8, 80, 300, 1500
+    g = torch.Generator(device="cuda").manual_seed(6)
+    # keys/queries with real alignment structure: frames are noisy copies of the token they belong to
+    k = torch.randn(b, c, tx, generator=g, device="cuda") * 3
+    owner = torch.sort(torch.randint(0, tx, (b, ty), generator=g, device="cuda"), dim=1).values
+    q = torch.gather(k, 2, owner[:, None, :].expand(b, c, ty)) + torch.randn(b, c, ty, generator=g, device="cuda")
+    t_x, t_y = np.full(b, tx, np.int32), np.full(b, ty, np.int32)
+    score = nc.ota_log_prob(q, k, 0.0005)
+    ref = nc_oracle.ota_log_prob(q.cpu().numpy(), k.cpu().numpy(), 0.0005)
+    assert _agreement(ma, score, ref, t_x, t_y) >= 0.9999
+
+
+def test_rejects_cpu_tensors(nc):
+    with pytest.raises(RuntimeError):
+        nc.gaussian_neg_cent(torch.zeros(1, 2, 3), torch.zeros(1, 2, 4), torch.zeros(1, 2, 4))
