@@ -27,8 +27,8 @@
 //     60-90 cycles of TMA issue per 128-byte row, 8x slower end to end; loads
 //     issued by the compute warps themselves doubled their per-frame latency.)
 //   * compute warps form a dataflow pipeline: warp w consumes the last row of
-//     warp w-1 through a 64-frame shared ring plus a progress flag, 16 frames at
-//     a time.  The diagonal band provides the pipeline skew for free (warp w
+//     warp w-1 through a 128-frame shared ring plus a progress flag, 16 or 32
+//     frames at a time.  The diagonal band provides the pipeline skew for free (warp w
 //     starts at frame 32*R*w); there is no CTA-wide barrier in the forward pass.
 //   * two forward forms, chosen by the host:
 //       lock-step  every lane works on the same frame; the neighbour exchange
@@ -51,7 +51,7 @@
 namespace alb {
 
 constexpr int kMaxWarps = 8;       // compute warps per CTA (an equal number of loader warps rides along)
-constexpr int kRing = 64;          // frames in a warp-boundary ring
+constexpr int kRing = 128;         // frames in a warp-boundary ring
 constexpr int kZeroChunk = 8192;   // bytes per zero-fill bulk store
 constexpr int kLanePad = 16;       // bytes of skew per lane inside a tile stage
 constexpr int kSkewLag = 4;        // frames lane l trails lane l-1 in the skewed form
@@ -339,7 +339,9 @@ template <int R, int TF, bool SKEW, int NWMAX, int MINB>
 __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasParams p)
 {
     constexpr int RW = 32 * R;
-    constexpr int UNIT = TF < 16 ? TF : 16;
+    // hand-off granularity between warps: a whole 32-frame tile when an utterance owns its SM (fewer flag/barrier round trips per
+    // frame), 16 frames in the register-capped throughput instances
+    constexpr int UNIT = (MINB == 1 && TF == 32) ? 32 : (TF < 16 ? TF : 16);
     constexpr int LANE_STRIDE = R * TF * 4 + kLanePad;
     constexpr int LAG31 = SKEW ? 31 * kSkewLag : 0;      // frames lane 31 trails lane 0
 
