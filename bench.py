@@ -117,8 +117,21 @@ def make_batch(seed: int, b: int, tx: int, ty: int):
 
 
 # --------------------------------------------------------------------------- CPU reference
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def load_cpu_reference():
     """oracle/_ref (the reference's own core.pyx, -fopenmp) when present, else the C port."""
+    use_all_host_threads()
     from oracle import mas
     ref = mas.load_reference_core("omp")
     if ref is not None:
@@ -143,7 +156,6 @@ def time_cpu(fn, values, t_x, t_y, steps: int, warmup: int):
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
     b, tx, ty, desc = WORKLOADS[args.workload]
     kind, fn, cores = load_cpu_reference()
     values, t_x, t_y = make_batch(1234 + 1, b, tx, ty)
@@ -200,15 +212,43 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
+    # The K timed steps are K kernel launches of ~50 us each; issued from Python they are launch-bound on the host, so they are
+    # captured once into a CUDA graph (same calls, same rotating buffers) and the replay is what is timed.
+    graph, launches = None, 0
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                step(0)                                              # this stream's workspace must exist before capture
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(args.steps):
+                    step(i)
+            launches = _lib.launch_count() - n0
+            graph.replay()                                           # warm replay
+            torch.cuda.synchronize()
+        except Exception as exc:                                     # capture not possible: time the eager loop
+            print("cuda graph capture failed, timing eager launches:", exc, file=sys.stderr)
+            graph = None
+    barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0 = _lib.launch_count()
     with ClockSampler(local_rank) as clk:
-        start.record()
-        for i in range(args.steps):
-            step(i)
-        end.record()
+        if graph is not None:
+            start.record()
+            graph.replay()
+            end.record()
+        else:
+            n0 = _lib.launch_count()
+            start.record()
+            for i in range(args.steps):
+                step(i)
+            end.record()
+            launches = _lib.launch_count() - n0
         torch.cuda.synchronize()
-    launches = _lib.launch_count() - n0
     ms = start.elapsed_time(end)
     barrier()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -272,7 +312,6 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             traffic = json.loads(tj.read_text()).get(args.workload)
         cpu = None
         if world == 1 and not args.no_cpu:
-            os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
             kind, fn, cores = load_cpu_reference()
             reps = 8
             times, ref_paths = time_cpu(fn, values_np, t_x, t_y, reps, 2)
@@ -286,7 +325,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s: B=%d T_text=%d T_mel=%d fp32 per GPU, full lengths (%s)" % (args.workload, b, tx, ty, desc),
                        "api": "monotonic_align.maximum_path(value, mask) on CUDA tensors, dense fp32 path out",
-                       "l2": "rotating %d input/output sets (%.0f MB) > 3x L2, no flush" % (nsets, nsets * per_set / 1e6)},
+                       "l2": "rotating %d input/output sets (%.0f MB) > 3x L2, no flush" % (nsets, nsets * per_set / 1e6),
+                       "launch": "K steps replayed from one CUDA graph" if graph is not None else "eager launches"},
             "utterances_per_sec": b * world / (ms_step * 1e-3),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -311,6 +351,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
