@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 
 namespace alb {
 extern thread_local char g_err[512];          // shared with mas_api.cu: alb200_last_error() reports both
@@ -255,6 +256,8 @@ static int nc_fail(int code, const char* msg)
 
 using namespace albnc;
 
+extern "C" int alb200_neg_cent_gaussian_tc(const float*, const float*, const float*, float*, int, int, int, int, void*);
+
 extern "C" {
 
 int alb200_neg_cent_gaussian(const float* z, const float* m_p, const float* logs_p, float* out, int b, int c, int tx, int ty, void* stream)
@@ -262,6 +265,9 @@ int alb200_neg_cent_gaussian(const float* z, const float* m_p, const float* logs
     if (!z || !m_p || !logs_p || !out || b < 0 || c <= 0 || tx <= 0 || ty <= 0) return nc_fail(ALB200_E_INVALID, "neg_cent_gaussian: null pointer or bad shape");
     if (b == 0) return 0;
     if (b > 65535) return nc_fail(ALB200_E_UNSUPPORTED, "neg_cent_gaussian: batch > 65535");
+    // default: tensor cores (tcgen05, 3xTF32, fp32 accumulate in TMEM).  ALB200_NC_FFMA=1 selects the CUDA-core kernel below
+    // (kept as the fixed-order fp32 cross-check of the tensor-core path, tests/test_neg_cent_gpu.py).
+    if (!getenv("ALB200_NC_FFMA")) return alb200_neg_cent_gaussian_tc(z, m_p, logs_p, out, b, c, tx, ty, stream);
     dim3 grid((ty + GBN - 1) / GBN, (tx + GBM - 1) / GBM, b);
     gaussian_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, m_p, logs_p, out, c, tx, ty);
     ++alb::g_launches;

@@ -19,7 +19,7 @@ PKG = Path(__file__).resolve().parent / "aligner_b200"
 CSRC = PKG / "csrc"
 LIB = PKG / "libaligner_b200.so"
 OBJ = CSRC / "_obj"
-SOURCES = ["mas_api.cu", "neg_cent.cu"]
+SOURCES = ["mas_api.cu", "neg_cent.cu", "neg_cent_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
