@@ -102,12 +102,14 @@ __global__ void __launch_bounds__(256, 1) gaussian_tc_kernel(const float* __rest
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-    const float* mb = m + (size_t)b * C * Tx;
-    const float* lb = logs + (size_t)b * C * Tx;
-    const float* zb = z + (size_t)b * C * Ty;
-    // producer roles: A row = tid % 128, channels 8*(tid/128) .. +7 of the chunk;  B row = tid, all 16 channels
+    // producer roles: A row = tid % 128, channels 8*(tid/128) .. +7 of the chunk;  B row = tid, all 16 channels.
+    // Rows past t_text / t_mel are clamped to a valid row: their products land in accumulator rows / columns the
+    // epilogue never stores, so no masking is needed on the fast path (only the K tail must be zero).
     const int arow = tid & 127, ahalf = tid >> 7;
-    const bool a_ok = x0 + arow < Tx, b_ok = y0 + tid < Ty;
+    const int ax = min(x0 + arow, Tx - 1), by = min(y0 + tid, Ty - 1);
+    const float* pm = m + (size_t)b * C * Tx + (size_t)(8 * ahalf) * Tx + ax;
+    const float* pl = logs + (size_t)b * C * Tx + (size_t)(8 * ahalf) * Tx + ax;
+    const float* pz = z + (size_t)b * C * Ty + by;
     const uint32_t a_off = (uint32_t)(arow >> 3) * 1024 + (uint32_t)(arow & 7) * 128;
     const uint32_t b_off = (uint32_t)(tid >> 3) * 1024 + (uint32_t)(tid & 7) * 128;
     const uint32_t a_x = (uint32_t)(arow & 7), b_x = (uint32_t)(tid & 7);
@@ -117,17 +119,30 @@ __global__ void __launch_bounds__(256, 1) gaussian_tc_kernel(const float* __rest
     // raw operands of one chunk, fetched one chunk ahead so the global-load latency hides behind the previous chunk's work
     float am[8], al[8], bz[16];
     auto fetch = [&](int c0) {
+        if (c0 + KCH <= C) {                                   // whole chunk: 32 unconditional strided loads
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int c = c0 + 8 * ahalf + q;
-            const bool ok = a_ok && c < C;
-            am[q] = ok ? mb[(size_t)c * Tx + x0 + arow] : 0.f;
-            al[q] = ok ? lb[(size_t)c * Tx + x0 + arow] : __int_as_float(0x7f800000);   // +inf -> s2 = exp(-inf) = 0 for padding
+            for (int q = 0; q < 8; ++q) { am[q] = pm[(size_t)q * Tx]; al[q] = pl[(size_t)q * Tx]; }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) bz[q] = pz[(size_t)q * Ty];
+        } else {                                               // K tail: channels >= C contribute exact zeros
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const bool ok = c0 + 8 * ahalf + q < C;
+                am[q] = ok ? pm[(size_t)q * Tx] : 0.f;
+                al[q] = ok ? pl[(size_t)q * Tx] : __int_as_float(0x7f800000);   // +inf marks padding: s2 = 0, no row term
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) bz[q] = (c0 + q < C) ? pz[(size_t)q * Ty] : 0.f;
         }
+        pm += (size_t)KCH * Tx; pl += (size_t)KCH * Tx; pz += (size_t)KCH * Ty;
+    };
+    // TF32 split: hi keeps the top 19 bits (what the tensor core reads), lo = v - hi is exact in fp32 and is itself read
+    // truncated, so hi + lo carries ~21 mantissa bits of v
+    auto split4 = [&](const float (&v)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int c = c0 + q;
-            bz[q] = (b_ok && c < C) ? zb[(size_t)c * Ty + y0 + tid] : 0.f;
+        for (int q = 0; q < 4; ++q) {
+            hi[q] = __float_as_uint(v[q]) & 0xffffe000u;
+            lo[q] = __float_as_uint(v[q] - __uint_as_float(hi[q]));
         }
     };
     fetch(0);
@@ -142,19 +157,15 @@ __global__ void __launch_bounds__(256, 1) gaussian_tc_kernel(const float* __rest
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const float mm = am[2 * j + h], lg = al[2 * j + h];
-                float s2 = 0.f, ms2 = 0.f;
-                if (lg != __int_as_float(0x7f800000)) {
-                    s2 = expf(-2.f * lg);
-                    ms2 = mm * s2;
-                    rsum += (-0.9189385332046727f - lg) - 0.5f * mm * ms2;
-                }
+                const bool pad = (lg == __int_as_float(0x7f800000));
+                const float s2 = pad ? 0.f : __expf(-2.f * lg);
+                const float ms2 = mm * s2;
+                rsum += pad ? 0.f : ((-0.9189385332046727f - lg) - 0.5f * mm * ms2);
                 v[2 * h] = s2; v[2 * h + 1] = ms2;
             }
             uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { hi[q] = to_tf32(v[q]); lo[q] = to_tf32(v[q] - __uint_as_float(hi[q])); }
-            const uint32_t chunk = (uint32_t)(4 * ahalf + j);                   // 16-byte chunk index along K
-            const uint32_t off = a_off + ((chunk ^ a_x) << 4);
+            split4(v, hi, lo);
+            const uint32_t off = a_off + ((((uint32_t)(4 * ahalf + j)) ^ a_x) << 4);   // 16-byte chunk index along K, swizzled
             sts128u(sA_hi + off, hi[0], hi[1], hi[2], hi[3]);
             sts128u(sA_lo + off, lo[0], lo[1], lo[2], lo[3]);
         }
@@ -168,8 +179,7 @@ __global__ void __launch_bounds__(256, 1) gaussian_tc_kernel(const float* __rest
                 v[2 * h] = -0.5f * zz * zz; v[2 * h + 1] = zz;
             }
             uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { hi[q] = to_tf32(v[q]); lo[q] = to_tf32(v[q] - __uint_as_float(hi[q])); }
+            split4(v, hi, lo);
             const uint32_t off = b_off + (((uint32_t)j ^ b_x) << 4);
             sts128u(sB_hi + off, hi[0], hi[1], hi[2], hi[3]);
             sts128u(sB_lo + off, lo[0], lo[1], lo[2], lo[3]);
