@@ -257,6 +257,7 @@ static int nc_fail(int code, const char* msg)
 using namespace albnc;
 
 extern "C" int alb200_neg_cent_gaussian_tc(const float*, const float*, const float*, float*, int, int, int, int, void*);
+extern "C" int alb200_neg_cent_ota_tc(const float*, const float*, const float*, const int32_t*, float*, float, int, int, int, int, void*);
 
 extern "C" {
 
@@ -282,6 +283,9 @@ int alb200_neg_cent_ota(const float* queries, const float* keys, const float* pr
     if (!queries || !keys || !out || b < 0 || c <= 0 || tx <= 0 || ty <= 0) return nc_fail(ALB200_E_INVALID, "neg_cent_ota: null pointer or bad shape");
     if (b == 0) return 0;
     if (b > 65535) return nc_fail(ALB200_E_UNSUPPORTED, "neg_cent_ota: batch > 65535");
+    // default: tensor cores; the log-softmax over the text axis is done on the accumulator in tensor memory, which holds
+    // 512 tokens.  Longer texts (and ALB200_NC_FFMA=1) take the CUDA-core kernel below.
+    if (tx <= 512 && !getenv("ALB200_NC_FFMA")) return alb200_neg_cent_ota_tc(queries, keys, prior, x_lengths, out, temperature, b, c, tx, ty, stream);
     size_t fixed = ((size_t)c * OBN + (size_t)c * OBX + OBN + 2 * 8 * OBN) * sizeof(float);
     size_t dbytes = (size_t)tx * (OBN + 1) * sizeof(float);
     int optin = 0, dev = 0;

@@ -63,6 +63,20 @@ def test_ota_matches_fp64(nc, b, c, tx, ty, with_prior, with_len):
         assert torch.allclose(p, torch.ones_like(p), atol=1e-5)
 
 
+@pytest.mark.parametrize("b,c,tx,ty", [(2, 192, 200, 1000), (2, 50, 600, 300), (1, 7, 513, 129)])
+def test_tensor_core_and_cuda_core_paths_agree(nc, monkeypatch, b, c, tx, ty):
+    """The tcgen05 kernels (default) against the fixed-order FFMA kernels (ALB200_NC_FFMA=1): two independent implementations."""
+    g = torch.Generator(device="cuda").manual_seed(7 + tx)
+    z = torch.randn(b, c, ty, generator=g, device="cuda")
+    m = torch.randn(b, c, tx, generator=g, device="cuda")
+    logs = torch.rand(b, c, tx, generator=g, device="cuda") * 1.5 - 1.0
+    tc_g, tc_o = nc.gaussian_neg_cent(z, m, logs), nc.ota_log_prob(z, m, 0.0005)
+    monkeypatch.setenv("ALB200_NC_FFMA", "1")
+    ff_g, ff_o = nc.gaussian_neg_cent(z, m, logs), nc.ota_log_prob(z, m, 0.0005)
+    assert (tc_g - ff_g).abs().max() <= TOL * ff_g.abs().max()
+    assert (tc_o - ff_o).abs().max() <= TOL * ff_o.abs().max()
+
+
 def _agreement(ma, score_gpu, score_ref64, t_x, t_y):
     ref32 = np.ascontiguousarray(score_ref64.astype(np.float32))
     want = np.zeros(ref32.shape, np.int32)
