@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <type_traits>
 
 namespace alb {
 extern thread_local char g_err[512];
@@ -84,6 +85,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// exp(x) for the variance term: one FMUL + one MUFU.EX2 (2^-22 relative error, far inside the 1e-5 budget)
+__device__ __forceinline__ float fast_exp(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
 }
 // TF32 split: hi keeps the top 19 bits (what the tensor core reads), lo = v - hi is exact in fp32 and is itself read
 // truncated, so hi + lo carries ~21 mantissa bits of v
@@ -163,28 +170,32 @@ __global__ void __launch_bounds__(256, 1) nc_tc_kernel(const TcParams p)
         const float* pb1 = MODE == 0 ? p.b_src1 + (size_t)b * C * Tx + bx : nullptr;
         float cacc = 0.f;                                    // colterm (gaussian) / |k_x|^2 (ota) of text row bx
 
-        float av[ACH], bv0[CPC], bv1[MODE == 0 ? CPC : 1];
-        auto fetch = [&](int c0) {
+        // raw operands of two chunks: chunk i+1 is fetched BEFORE chunk i is transformed, so a full chunk of work (and the
+        // MMA wait) hides the global-load latency; two register sets, selected at compile time (loop unrolled by two)
+        float av[2][ACH], bv0[2][CPC], bv1[2][MODE == 0 ? CPC : 1];
+        auto fetch = [&](auto bufc, int c0) {
+            constexpr int B_ = decltype(bufc)::value;
             if (c0 + CPC <= C) {                             // whole chunk: unconditional strided loads
 #pragma unroll
-                for (int q = 0; q < ACH; ++q) av[q] = pa[(size_t)q * Ty];
+                for (int q = 0; q < ACH; ++q) av[B_][q] = pa[(size_t)q * Ty];
 #pragma unroll
-                for (int q = 0; q < CPC; ++q) { bv0[q] = pb0[(size_t)q * Tx]; if (MODE == 0) bv1[q] = pb1[(size_t)q * Tx]; }
+                for (int q = 0; q < CPC; ++q) { bv0[B_][q] = pb0[(size_t)q * Tx]; if (MODE == 0) bv1[B_][q] = pb1[(size_t)q * Tx]; }
             } else {                                         // K tail: channels >= C contribute exact zeros
 #pragma unroll
-                for (int q = 0; q < ACH; ++q) av[q] = (c0 + ACH * ahalf + q < C) ? pa[(size_t)q * Ty] : 0.f;
+                for (int q = 0; q < ACH; ++q) av[B_][q] = (c0 + ACH * ahalf + q < C) ? pa[(size_t)q * Ty] : 0.f;
 #pragma unroll
                 for (int q = 0; q < CPC; ++q) {
                     const bool ok = c0 + q < C;
-                    bv0[q] = ok ? pb0[(size_t)q * Tx] : 0.f;
-                    if (MODE == 0) bv1[q] = ok ? pb1[(size_t)q * Tx] : __int_as_float(0x7f800000);   // +inf marks padding
+                    bv0[B_][q] = ok ? pb0[(size_t)q * Tx] : 0.f;
+                    if (MODE == 0) bv1[B_][q] = ok ? pb1[(size_t)q * Tx] : __int_as_float(0x7f800000);   // +inf marks padding
                 }
             }
             pa += (size_t)CPC * Ty; pb0 += (size_t)CPC * Tx;
             if (MODE == 0) pb1 += (size_t)CPC * Tx;
         };
-        fetch(0);
-        for (int i = 0; i < nchunks; ++i, ++it) {
+        auto chunk = [&](auto bufc, auto nextc, int i) {
+            constexpr int B_ = decltype(bufc)::value;
+            if (i + 1 < nchunks) fetch(nextc, (i + 1) * CPC);
             const int st = it & 1;
             if (it >= 2) mbar_wait(bar_empty0 + 8 * st, (uint32_t)(((it >> 1) - 1) & 1));
             const uint32_t sA_hi = base + st * STAGE, sA_lo = sA_hi + A_TILE, sB_hi = sA_lo + A_TILE, sB_lo = sB_hi + B_TILE;
@@ -194,10 +205,10 @@ __global__ void __launch_bounds__(256, 1) nc_tc_kernel(const TcParams p)
                 float v[4];
                 if (MODE == 0) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) { const float zz = av[2 * j + h]; v[2 * h] = -0.5f * zz * zz; v[2 * h + 1] = zz; }
+                    for (int h = 0; h < 2; ++h) { const float zz = av[B_][2 * j + h]; v[2 * h] = -0.5f * zz * zz; v[2 * h + 1] = zz; }
                 } else {
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) { v[h] = av[4 * j + h]; if (pass == 0) qn = fmaf(v[h], v[h], qn); }
+                    for (int h = 0; h < 4; ++h) { v[h] = av[B_][4 * j + h]; if (pass == 0) qn = fmaf(v[h], v[h], qn); }
                 }
                 uint32_t hi[4], lo[4];
                 split4(v, hi, lo);
@@ -205,31 +216,32 @@ __global__ void __launch_bounds__(256, 1) nc_tc_kernel(const TcParams p)
                 sts128u(sA_hi + off, hi[0], hi[1], hi[2], hi[3]);
                 sts128u(sA_lo + off, lo[0], lo[1], lo[2], lo[3]);
             }
-            // ---- B (text side): 8 chunks of 16 bytes per thread
+            // ---- B (text side): 8 chunks of 16 bytes per thread; rows >= NT are never read by the MMA
+            if (tid < ncols) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float v[4];
-                if (MODE == 0) {
+                for (int j = 0; j < 8; ++j) {
+                    float v[4];
+                    if (MODE == 0) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const float mm = bv0[2 * j + h], lg = bv1[2 * j + h];
-                        const bool pad = (lg == __int_as_float(0x7f800000));
-                        const float s2 = pad ? 0.f : __expf(-2.f * lg);
-                        const float ms2 = mm * s2;
-                        cacc += pad ? 0.f : ((-0.9189385332046727f - lg) - 0.5f * mm * ms2);
-                        v[2 * h] = s2; v[2 * h + 1] = ms2;
+                        for (int h = 0; h < 2; ++h) {
+                            const float mm = bv0[B_][2 * j + h], lg = bv1[B_][2 * j + h];
+                            const bool pad = (lg == __int_as_float(0x7f800000));
+                            const float s2 = pad ? 0.f : fast_exp(-2.f * lg);
+                            const float ms2 = mm * s2;
+                            cacc += pad ? 0.f : ((-0.9189385332046727f - lg) - 0.5f * mm * ms2);
+                            v[2 * h] = s2; v[2 * h + 1] = ms2;
+                        }
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) { v[h] = bv0[B_][4 * j + h]; cacc = fmaf(v[h], v[h], cacc); }
                     }
-                } else {
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) { v[h] = bv0[4 * j + h]; cacc = fmaf(v[h], v[h], cacc); }
+                    uint32_t hi[4], lo[4];
+                    split4(v, hi, lo);
+                    const uint32_t off = b_off + (((uint32_t)j ^ b_x) << 4);
+                    sts128u(sB_hi + off, hi[0], hi[1], hi[2], hi[3]);
+                    sts128u(sB_lo + off, lo[0], lo[1], lo[2], lo[3]);
                 }
-                uint32_t hi[4], lo[4];
-                split4(v, hi, lo);
-                const uint32_t off = b_off + (((uint32_t)j ^ b_x) << 4);
-                sts128u(sB_hi + off, hi[0], hi[1], hi[2], hi[3]);
-                sts128u(sB_lo + off, lo[0], lo[1], lo[2], lo[3]);
             }
-            if (i + 1 < nchunks) fetch((i + 1) * CPC);                            // in flight across the barrier and the MMA issue
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy stores -> visible to the tensor core
             __syncthreads();
             if (tid == 0) {
@@ -246,6 +258,14 @@ __global__ void __launch_bounds__(256, 1) nc_tc_kernel(const TcParams p)
                 mma_commit(bar_empty0 + 8 * st);                                    // stage reusable when these MMAs have read it
                 if (pass == npass - 1 && i == nchunks - 1) mma_commit(bar_accum);   // accumulator complete
             }
+            ++it;
+        };
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        fetch(I0{}, 0);
+        for (int i = 0; i < nchunks; i += 2) {
+            chunk(I0{}, I1{}, i);
+            if (i + 1 < nchunks) chunk(I1{}, I0{}, i + 1);
         }
         if (pass * NPASS + tid < NMAX) colv[pass * NPASS + tid] = cacc;
     }
@@ -268,10 +288,21 @@ __global__ void __launch_bounds__(256, 1) nc_tc_kernel(const TcParams p)
                 uint32_t r[16];
                 tmem_ld16(tlane + (uint32_t)(16 * g), r);
                 if (y_ok) {
+                    float* o = ob + (size_t)(16 * g) * Ty;
+                    const float4* cv = reinterpret_cast<const float4*>(colv + 16 * g);
+                    if (16 * g + 16 <= ntext) {                  // whole group: no per-token checks; 32 lanes = 32 consecutive frames
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int xl = 16 * g + j;
-                        if (xl < ntext) ob[(size_t)xl * Ty] = __uint_as_float(r[j]) + colv[xl];     // 32 lanes = 32 consecutive frames
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 c4 = cv[j4];
+                            o[0] = __uint_as_float(r[4 * j4]) + c4.x; o += Ty;
+                            o[0] = __uint_as_float(r[4 * j4 + 1]) + c4.y; o += Ty;
+                            o[0] = __uint_as_float(r[4 * j4 + 2]) + c4.z; o += Ty;
+                            o[0] = __uint_as_float(r[4 * j4 + 3]) + c4.w; o += Ty;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (16 * g + j < ntext) o[(size_t)j * Ty] = __uint_as_float(r[j]) + colv[16 * g + j];
                     }
                 }
             }
