@@ -87,23 +87,29 @@ struct Config {
 };
 
 // Picks rows-per-lane, tile width, ring depth and where the direction bits live.
-//   latency regime   (b <= #SM): one CTA per SM, <= 4 warps when possible (one per
-//                    scheduler), deep ring, bits in shared memory.
-//   throughput regime (b > #SM): two CTAs per SM so one item's backtrack overlaps
-//                    another item's streaming.
+//   latency regime   (b <= #SM): one CTA per SM, <= 4 compute warps when possible (one per scheduler), 255-register
+//                    instance, deepest ring that fits, bits in shared memory.
+//   throughput regime (b > #SM): 4 rows per lane, and the smallest ring (>= 2 stages) that lets the 128-register
+//                    instances reach their register-limited occupancy (8 / compute-warps CTAs per SM), so that about 8
+//                    compute warps per SM hide each other's latency and one item's backtrack overlaps others' streaming.
 static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool want_dur, Config* c)
 {
+    const bool latency = b <= di.sms;
     int R, NW;
     if (tx <= 32) { R = 1; NW = 1; }
-    else if (tx <= 1024) {
-        int raw = (tx + 127) / 128;
-        if (raw < 2) raw = 2;
-        R = raw <= 4 ? raw : (raw <= 6 ? 6 : 8);
+    else if (latency) {
+        // one warp per scheduler: <= 4 compute warps, as few rows per lane as that allows
+        if (tx <= 1024) {
+            int raw = (tx + 127) / 128;
+            if (raw < 2) raw = 2;
+            R = raw <= 4 ? raw : (raw <= 6 ? 6 : 8);
+        } else R = tx <= 2048 ? 8 : 16;
         NW = (tx + 32 * R - 1) / (32 * R);
-    } else if (tx <= 2048) {
-        R = 8; NW = (tx + 255) / 256;
     } else {
-        R = 16; NW = (tx + 511) / 512;
+        // throughput: 4 rows per lane measured best (profiles/r01_shape_sweep.json); what matters is ~8 resident compute
+        // warps per SM, i.e. as many CTAs as the 128-register instances allow
+        R = tx <= 64 ? 2 : (tx <= 512 ? 4 : (tx <= 2048 ? 8 : 16));
+        NW = (tx + 32 * R - 1) / (32 * R);
     }
     int f_tf = 0, f_ns = 0, f_bits = -1, f_skew = -1;
     if (const char* f = getenv("ALB200_FORCE")) {   // "R,TF,NS,bits_smem,skew" -- tuning / tests only
@@ -116,34 +122,35 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
         return fail(ALB200_E_UNSUPPORTED, "t_x=%s%lld needs too many compute warps at %lld rows per lane", "", tx, R);
     const int nblk = (ty + 31) / 32;
     const int per_sm = di.smem_optin + 1024;                   // 228 KB on sm_100
-    const bool latency = b <= di.sms;
-    const int budgets[2] = { latency ? di.smem_optin : per_sm / 2 - 1024, di.smem_optin };
     const int tfs[3] = { R >= 16 ? 16 : 32, R == 1 ? 32 : 16, R >= 8 ? 8 : (R == 1 ? 32 : 16) };
     int best_tf = 0, best_ns = 0, best_bits = 0;
-    for (int pass = 0; pass < 2 && !best_tf; ++pass) {         // pass 0: want >= 3 stages, pass 1: accept 2
-        for (int bi = 0; bi < 2 && !best_tf; ++bi) {
-            if (bi == 1 && budgets[1] == budgets[0]) break;
-            for (int ti = 0; ti < 3 && !best_tf; ++ti) {
-                if (f_tf && tfs[ti] != f_tf) continue;
-                for (int bs = 1; bs >= 0 && !best_tf; --bs) {
-                    if (f_bits >= 0 && bs != f_bits) continue;
-                    SmemLayout L0 = make_layout(NW, 0, R, tfs[ti], bs, nblk, want_dur);
-                    const int64_t fixed = (int64_t)L0.total + 2 * NW * 8 * 8;  // + up to 8 full and 8 empty barriers per warp
-                    const int64_t ring = (int64_t)NW * L0.stage_bytes;
-                    int64_t ns = (budgets[bi] - fixed) / ring;
-                    const int cap = latency ? 8 : 4;
-                    if (ns > cap) ns = cap;
-                    if (f_ns) { if (ns < f_ns) continue; ns = f_ns; }
-                    if (ns >= (pass == 0 ? 3 : 2)) { best_tf = tfs[ti]; best_ns = (int)ns; best_bits = bs; }
-                }
-            }
+    auto try_fit = [&](int tf, int ns, int bs, int budget) -> bool {
+        if (f_tf && tf != f_tf) return false;
+        if (f_ns && ns != f_ns) return false;
+        if (f_bits >= 0 && bs != f_bits) return false;
+        const SmemLayout L = make_layout(NW, ns, R, tf, bs, nblk, want_dur);
+        if ((int64_t)L.total > budget) return false;
+        best_tf = tf; best_ns = ns; best_bits = bs;
+        return true;
+    };
+    if (latency) {
+        // deepest ring that fits one CTA per SM, bits in shared memory when possible
+        for (int pass = 0; pass < 2 && !best_tf; ++pass)
+            for (int ti = 0; ti < 3 && !best_tf; ++ti)
+                for (int bs = 1; bs >= 0 && !best_tf; --bs)
+                    for (int ns = 8; ns >= (pass == 0 ? 3 : 2) && !best_tf; --ns) try_fit(tfs[ti], ns, bs, di.smem_optin);
+    } else {
+        const int reg_occ = NW <= 4 ? 8 / (NW == 3 ? 4 : NW) : 1;          // 128-register instances: 512 compute+loader threads... 8/NW CTAs
+        for (int occ = reg_occ; occ >= 1 && !best_tf; --occ) {
+            const int budget = per_sm / occ - 1024;
+            for (int ti = 0; ti < 3 && !best_tf; ++ti)
+                for (int ns = 3; ns >= 2 && !best_tf; --ns)
+                    for (int bs = 1; bs >= 0 && !best_tf; --bs) try_fit(tfs[ti], ns, bs, budget);
         }
     }
     if (!best_tf)
         return fail(ALB200_E_UNSUPPORTED, "t_x=%s%lld does not fit the shared-memory ring (max about 3300)", "", tx);
     c->R = R; c->TF = best_tf; c->NW = NW; c->NS = best_ns; c->bits_smem = best_bits;
-    // latency regime: the lane-skewed (systolic) forward keeps the shuffle off the per-frame chain;
-    // throughput regime: several CTAs per SM already hide it, and the lock-step form has no pipeline fill.
     // skewed (systolic) forward: the shuffle leaves the per-frame chain, but every lane adds 4 frames of pipeline fill
     // and every warp hand-off another 124, so it only pays when one compute warp covers the whole text axis.
     c->skew = f_skew >= 0 ? f_skew : ((latency && NW == 1) ? 1 : 0);
@@ -160,7 +167,7 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     int occ = 0;
     ALB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->fn, 2 * NW * 32, c->smem));
     if (occ < 1) return fail(ALB200_E_UNSUPPORTED, "kernel does not fit on an SM (smem %s%lld bytes)", "", c->smem);
-    if (!latency && occ > 4) occ = 4;
+    if (!latency && occ > 8) occ = 8;
     c->occ = occ;
     return 0;
 }

@@ -18,6 +18,7 @@ PEAK = 6549.1
 
 
 def bench(b, tx, ty, force, ragged=False, reps=30, dense=True):
+    dense = dense and os.environ.get("DENSE", "1") == "1"
     if force:
         os.environ["ALB200_FORCE"] = force
     else:
@@ -73,8 +74,9 @@ def main():
                                       "3,32,4,1,1", "4,32,4,1,1", "1,32,4,1,1", "8,32,2,1,1"]),
         "c3": (32, 300, 1500, False, [None, "3,32,3,0,0", "3,32,3,0,1", "3,32,4,0,1", "4,32,3,0,1", "6,32,2,0,1", "3,16,6,0,1"]),
         "c4": (8, 1000, 6000, False, [None, "8,16,2,0,0", "8,16,2,0,1", "8,16,3,0,1", "4,16,2,0,1", "6,16,2,0,1"]),
-        "c5a": (1024, 400, 2000, True, [None, "4,16,3,0,1", "3,16,3,0,0", "3,16,3,0,1", "2,16,2,0,0", "2,16,2,0,1"]),
-        "c5b": (4096, 200, 1000, False, [None, "2,32,2,1,0", "2,32,2,1,1", "4,32,2,1,0", "4,32,2,1,1"]),
+        "c5a": (2048, 400, 2000, True, [None, "4,16,3,0,0", "8,16,2,0,0", "8,16,3,0,0", "8,8,3,0,0", "8,8,4,0,0", "6,16,2,0,0", "8,32,2,0,0"]),
+        "c5b": (4096, 200, 1000, False, [None, "4,16,2,0,0", "4,16,3,0,0", "4,32,2,0,0", "4,32,2,1,0", "6,16,2,0,0", "8,16,2,0,0", "3,16,2,0,0"]),
+        "c5c": (4096, 100, 800, False, [None, "2,16,2,0,0", "2,16,3,0,0", "2,32,2,0,0", "4,16,2,0,0", "4,32,2,1,0", "1,32,2,1,0"]),
     }
     for name, (b, tx, ty, ragged, forces) in plans.items():
         if which != "all" and which != name:
