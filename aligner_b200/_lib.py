@@ -9,7 +9,8 @@ import ctypes
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libaligner_b200.so"
+import os as _os
+LIB_PATH = Path(_os.environ["ALB200_LIB"]) if _os.environ.get("ALB200_LIB") else _PKG / "libaligner_b200.so"   # ALB200_LIB: A/B builds while tuning
 
 OK = 0
 E_INVALID, E_UNSUPPORTED, E_CUDA, E_LENGTHS, E_NO_DEVICE = -1, -2, -3, -4, -5

@@ -237,7 +237,7 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
     {
         const SmemLayout L = make_layout(c.NW, c.NS, c.R, c.TF, c.bits_smem, p.nblk, durations != nullptr);
         p.off_full = L.off_full; p.off_empty = L.off_empty; p.off_flags = L.off_flags; p.off_misc = L.off_misc; p.off_bnd = L.off_bnd;
-        p.off_zero = L.off_zero; p.off_ring = L.off_ring; p.off_bits = L.off_bits; p.off_dur = L.off_dur; p.stage_bytes = L.stage_bytes;
+        p.off_zero = L.off_zero; p.off_ring = L.off_ring; p.off_bits = L.off_bits; p.off_dur = L.off_dur; p.off_bt = L.off_bt; p.stage_bytes = L.stage_bytes;
     }
     p.aligned = ((reinterpret_cast<uintptr_t>(values) & 15) == 0 && (ty & 3) == 0) ? 1 : 0;
     if (getenv("ALB200_FORCE_UNALIGNED")) p.aligned = 0;
@@ -264,7 +264,11 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
             for (int w = 0; w < c.NW; ++w) fprintf(stderr, " w%d fwd %lld (end@%lld)", w, d[w * 2 + 1] - d[w * 2], d[w * 2 + 1] - t0);
             for (int w = c.NW; w < 2 * c.NW; ++w) fprintf(stderr, " ld%d end@%lld", w - c.NW, d[w * 2 + 1] - t0);
             fprintf(stderr, " | item done @%lld\n", d[2 * kMaxWarps * 2 + 1] - t0);
-            for (int w = 0; w < c.NW; ++w) {
+            {
+                long long* e = h + (size_t)c.grid * (2 * kMaxWarps + 2) * 2 + ((size_t)cta * kMaxWarps + (kMaxWarps - 1)) * 4;
+                if (e[3] < 0) fprintf(stderr, "[alb200 dbg]   backtrack: %lld blocks; per block: select+fixups %lld, walk %lld, publish %lld cycles\n", -e[3], e[0], e[1], e[2]);
+            }
+            for (int w = 0; w < c.NW && w < kMaxWarps - 1; ++w) {
                 long long* e = h + (size_t)c.grid * (2 * kMaxWarps + 2) * 2 + ((size_t)cta * kMaxWarps + w) * 4;
                 if (e[3] > 0)
                     fprintf(stderr, "[alb200 dbg]   w%d: %lld units; per unit: wait-full %lld, polls %lld, compute %lld, other %lld cycles\n", w, e[3],

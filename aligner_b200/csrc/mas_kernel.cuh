@@ -52,7 +52,7 @@ namespace alb {
 
 constexpr int kMaxWarps = 8;       // compute warps per CTA (an equal number of loader warps rides along)
 constexpr int kRing = 128;         // frames in a warp-boundary ring
-constexpr int kZeroChunk = 8192;   // bytes per zero-fill bulk store
+constexpr int kZeroChunk = 7680;   // bytes per zero-fill bulk store (60 x 128; sized so 2 CTAs x 3 stages still fit an SM at t_x = 400)
 constexpr int kLanePad = 16;       // bytes of skew per lane inside a tile stage
 constexpr int kSkewLag = 4;        // frames lane l trails lane l-1 in the skewed form
 constexpr int kProgDone = 0x3fffffff;
@@ -88,11 +88,11 @@ struct MasParams {
     int nblk;                   // ceil(Ty/32)
     int aligned;                // values base and Ty allow 16-byte copies
     float neg;
-    uint32_t off_full, off_empty, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, stage_bytes;   // make_layout(), done on the host
+    uint32_t off_full, off_empty, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, off_bt, stage_bytes;   // make_layout(), done on the host
 };
 
 struct SmemLayout {
-    uint32_t off_full, off_empty, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, total;
+    uint32_t off_full, off_empty, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, off_bt, total;
     uint32_t stage_bytes;
 };
 
@@ -113,6 +113,7 @@ __host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF,
     L.off_ring = alb_align(o, 128); o = L.off_ring + NW * NS * L.stage_bytes;
     L.off_bits = alb_align(o, 16);  o = L.off_bits + (bits_smem ? (uint32_t)nblk * NW * RW * 4 : 0);
     L.off_dur = alb_align(o, 16);   o = L.off_dur + (want_dur ? NW * RW * 4 : 0);
+    L.off_bt = alb_align(o, 16);    o = L.off_bt + (uint32_t)nblk * 8 + 16;                 // backtrack hand-off: (token, step mask) per 32-frame block + cursor
     L.total = alb_align(o, 16);
     return L;
 }
@@ -354,8 +355,8 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     const int TXS = NW * RW;
     const int nthr = blockDim.x;
     const bool bits_smem = (p.bits_ws == nullptr);
-    struct { uint32_t off_full, off_empty, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, stage_bytes; } L =
-        { p.off_full, p.off_empty, p.off_flags, p.off_misc, p.off_bnd, p.off_zero, p.off_ring, p.off_bits, p.off_dur, p.stage_bytes };
+    struct { uint32_t off_full, off_empty, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, off_bt, stage_bytes; } L =
+        { p.off_full, p.off_empty, p.off_flags, p.off_misc, p.off_bnd, p.off_zero, p.off_ring, p.off_bits, p.off_dur, p.off_bt, p.stage_bytes };
 
     const uint32_t smem0 = smem_u32(smem);
     const uint32_t full0 = smem0 + L.off_full + w * NS * 8;
@@ -370,6 +371,9 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     uint32_t* bits = bits_smem ? reinterpret_cast<uint32_t*>(smem + L.off_bits)
                                : p.bits_ws + (int64_t)blockIdx.x * p.bits_slot_words;
     int* durS = reinterpret_cast<int*>(smem + L.off_dur);
+    volatile int* btTok = reinterpret_cast<volatile int*>(smem + L.off_bt);          // [nblk] token at the last frame of each block
+    volatile uint32_t* btMov = reinterpret_cast<volatile uint32_t*>(smem + L.off_bt) + p.nblk;   // [nblk] frames at which the path steps down (bit 31-k)
+    const uint32_t bt_cur_a = smem0 + L.off_bt + 8 * (uint32_t)p.nblk;              // lowest block the walker has published
 
     // ---- one-time setup
     if (!is_loader && lane == 0)
@@ -432,6 +436,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         }
         if (!valid) { t_x = 0; t_y = 0; }
         if (dbg_on && first_item && lane == 0) dbg[wid * 2] = clock64();
+        if (tid == 0) st_flag(bt_cur_a, ((t_y - 1) >> 5) + 1);     // nothing published yet (ordered by the barrier after the forward pass)
 
         // ---- geometry of this warp's slice of the band
         const int x0 = w * RW;
@@ -592,53 +597,106 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         if (dbg_on && first_item && lane == 0) dbg[wid * 2 + 1] = clock64();
         __syncthreads();
 
-        // ================= backtrack (warp 0) =================
+        // ================= backtrack =================
+        // Warp 0 walks: 32 frames per step, one find-leading-one chain per step DOWN (about t_x/t_y of the frames).  It only
+        // publishes (token at the block's last frame, mask of step frames) per block; the other warps turn those into
+        // stores, so address arithmetic and memory traffic are off the serial chain.
+        const int top = (t_y - 1) >> 5;
         if (wid == 0) {
-            int tok0 = t_x - 1;
-            for (int blk = (t_y - 1) >> 5; blk >= 0; --blk) {
+            int tok0 = t_x - 1, base = tok0;
+            // direction words of rows (base - lane) and (base - 32 - lane): the next block's window starts at most 32 rows
+            // below this one's, so both candidates are fetched a block ahead and the load latency hides behind the walk
+            auto load_pair = [&](int blk, int bs, uint32_t& a, uint32_t& b2) {
+                const int ra = bs - lane, rb = bs - 32 - lane;
+                a = (ra > 0) ? bits[(int64_t)blk * TXS + ra] : 0u;      // row 0 can never step down (core.pyx:34 index != 0)
+                b2 = (rb > 0) ? bits[(int64_t)blk * TXS + rb] : 0u;
+            };
+            uint32_t wA = 0u, wB = 0u;
+            if (top >= 0) load_pair(top, base, wA, wB);
+            long long bA = 0, bB = 0, bC = 0, q0 = 0, q1 = 0, q2 = 0;
+            for (int blk = top; blk >= 0; --blk) {
+                if (dbg_on) q0 = clock64();
                 const int yb = blk << 5;
                 const int nvalid = (t_y - yb < 32) ? t_y - yb : 32;
-                const int row = tok0 - lane;
-                uint32_t wd = (row > 0) ? bits[(int64_t)blk * TXS + row] : 0u;      // row 0 can never step down (core.pyx:34 index != 0)
-                const int dg = row - yb;                                            // diagonal cell of this row: forced step (index == y)
-                if (row > 0 && dg >= 0 && dg < 32) wd |= (1u << dg);
-                if (nvalid < 32) wd &= (1u << nvalid) - 1u;
-                // Rows are left strictly in the order tok0, tok0-1, ...: every lane gathers the 32 direction words of the window
-                // (32 pipelined broadcasts) and replays the same scalar walk: on row j, the next step down is at the highest set
-                // bit at or below the current frame.  One find-leading-one chain per STEP (about t_x/t_y of the frames) instead of
-                // one dependent operation per FRAME, and no 32x32 bit transpose.
-                uint32_t moves = 0u;            // bit k set: the path steps down when going from frame k to k-1
-                uint32_t below = 0xffffffffu;   // frames not yet assigned to a row
+                // the 64-row window goes through shared memory (warp 0's boundary ring is idle now): every lane patches the
+                // diagonal cells of its two rows (forced step, index == y) and stores them; the walk then reads consecutive words
+                const int ra = base - lane, rb = base - 32 - lane;
+                const int da = ra - yb, db = rb - yb;
+                if (ra > 0 && da >= 0 && da < 32) wA |= (1u << da);
+                if (rb > 0 && db >= 0 && db < 32) wB |= (1u << db);
+                const uint32_t wbuf = bnd_a + (uint32_t)(blk & 1) * 256;
+                __syncwarp();
+                // stored bit-REVERSED (frame k at bit 31-k): "next step at the highest frame not above the current one" becomes
+                // "lowest set bit", which is two plain ALU ops (t & -t); find-leading-one is a slow-pipe instruction
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wbuf + 4 * lane), "r"(__brev(wA)) : "memory");
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wbuf + 128 + 4 * lane), "r"(__brev(wB)) : "memory");
+                __syncwarp();
+                const int shift = base - tok0;                    // 0..32: where this block's first row sits in the window
+                if (blk > 0) load_pair(blk - 1, tok0, wA, wB);    // next block's candidates, a block ahead
+                // Rows are left strictly in the order tok0, tok0-1, ...: on row j the next step down is at the highest set bit
+                // at or below the current frame.  Every lane replays the same scalar walk on broadcast loads that run three
+                // rows ahead, so the chain per STEP is and / find-leading-one / mask.
+                uint32_t moves = 0u;                                                // bit 31-k set: the path steps down when going from frame k to k-1
+                uint32_t below = (nvalid < 32) ? ~((1u << (32 - nvalid)) - 1u) : 0xffffffffu;   // (reversed) frames not yet assigned to a row
                 int nmove = 0;
-                bool walking = true;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {          // 16 rows at a time keeps the register footprint small
-                    if (!walking) break;
-                    uint32_t wj[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) wj[j] = __shfl_sync(0xffffffffu, wd, 16 * half + j);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const uint32_t t = wj[j] & below;
-                        if (t == 0u) { walking = false; break; }  // stays on this row down to the start of the block
-                        const int kq = 31 - __clz(t);             // frame of the step
-                        moves |= 1u << kq;
-                        below = (1u << kq) - 1u;                  // frames kq-1 .. 0 belong to the rows further down
-                        ++nmove;
-                    }
+                if (dbg_on) q1 = clock64();
+                // three broadcast loads in flight, registers rotated by unrolling (reads may run two words past the window: the
+                // boundary-ring region continues behind it, the values are never used)
+                uint32_t wadr = wbuf + 4u * (uint32_t)shift;
+                uint32_t w0, w1, w2;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(wadr));
+                asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(w1) : "r"(wadr));
+                asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(w2) : "r"(wadr));
+#define ALB_BT_STEP(W)                                                                                                  \
+    {                                                                                                                   \
+        const uint32_t t = (W) & below;               /* 0: stays on this row down to the start of the block */         \
+        const uint32_t lsb = t & (0u - t);            /* the step: highest remaining frame = lowest reversed bit */     \
+        moves |= lsb;                                                                                                   \
+        below = ~(lsb | (lsb - 1u));                  /* earlier frames go to the rows further down; t == 0 -> 0 */     \
+        wadr += 4u;                                                                                                     \
+        asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(W) : "r"(wadr));                                                \
+    }
+                // branch-free steps (a GPU does not speculate: a per-step exit test would put the branch latency on the chain);
+                // once a row has no step left, `below` is 0 and the remaining steps of the trio are no-ops
+                do {
+                    ALB_BT_STEP(w0)
+                    ALB_BT_STEP(w1)
+                    ALB_BT_STEP(w2)
+                } while (below != 0u);
+                nmove = __popc(moves);
+#undef ALB_BT_STEP
+                if (dbg_on) q2 = clock64();
+                if (lane == 0) {
+                    btTok[blk] = tok0;
+                    btMov[blk] = moves;
+                    st_flag(bt_cur_a, blk);                       // same lane, after the payload: in-order shared-memory pipe
                 }
-                const int mine_moves = __popc(moves & ~((2u << lane) - 1u));   // steps taken at frames above ours
+                base = tok0;
+                tok0 -= nmove;
+                if (dbg_on) { const long long q3 = clock64(); bA += q1 - q0; bB += q2 - q1; bC += q3 - q2; }
+            }
+            if (dbg_on && first_item && lane == 0 && top >= 0) {
+                long long* e = p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4;
+                e[0] = bA / (top + 1); e[1] = bB / (top + 1); e[2] = bC / (top + 1); e[3] = -(top + 1);
+            }
+        } else {
+            if (p.frame_tok != nullptr)
+                for (int yy = t_y + (tid - 32); yy < Ty; yy += nthr - 32) p.frame_tok[(int64_t)item * Ty + yy] = -1;
+            const int nemit = (nthr >> 5) - 1;                    // every warp but the walker
+            for (int blk = top - (wid - 1); blk >= 0; blk -= nemit) {
+                while (ld_flag(bt_cur_a) > blk) { }
+                const int tokb = btTok[blk];
+                const uint32_t moves = btMov[blk];
+                const int yb = blk << 5;
+                const int nvalid = (t_y - yb < 32) ? t_y - yb : 32;
                 if (lane < nvalid) {
-                    const int tok = tok0 - mine_moves;
+                    const int tok = tokb - __popc(moves & ((1u << (31 - lane)) - 1u));   // steps at frames above ours (mask is bit-reversed)
                     const int yy = yb + lane;
                     if (p.paths != nullptr) store_one(p.paths, item * item_elems + (int64_t)tok * Ty + yy, p.esize, p.one);
                     if (p.frame_tok != nullptr) p.frame_tok[(int64_t)item * Ty + yy] = tok;
                     if (p.durations != nullptr) atomicAdd(&durS[tok], 1);
                 }
-                tok0 -= nmove;
             }
-        } else if (p.frame_tok != nullptr) {
-            for (int yy = t_y + (tid - 32); yy < Ty; yy += nthr - 32) p.frame_tok[(int64_t)item * Ty + yy] = -1;
         }
         __syncthreads();
         if (p.durations != nullptr)
