@@ -54,13 +54,14 @@ static int device_info(DevInfo* out)
 }
 
 // ------------------------------------------------------------------ kernel table
-typedef void (*KernelFn)(const MasParams);
+typedef void (*KernelFn)(const MasParams, const CUtensorMap);
 struct KEntry { int R, TF, skew, nwmax, minb; KernelFn fn; };
 // lock-step form: a 255-register instance for the latency regime and a 128-register one for two CTAs per SM;
 // skewed form: latency regime only.
-#define ALB_K(R, TF) { R, TF, 0, 4, 1, mas_kernel<R, TF, false, 4, 1> }, { R, TF, 0, 4, 2, mas_kernel<R, TF, false, 4, 2> }, \
-                     { R, TF, 1, 4, 1, mas_kernel<R, TF, true, 4, 1> }
-#define ALB_K8(R, TF) { R, TF, 0, 8, 1, mas_kernel<R, TF, false, 8, 1> }, { R, TF, 1, 8, 1, mas_kernel<R, TF, true, 8, 1> }
+#define ALB_K(R, TF) { R, TF, 0, 4, 1, mas_kernel<R, TF, false, 4, 1> }, { R, TF, 0, 4, 2, mas_kernel<R, TF, false, 4, 2> }
+#define ALB_KS(R) { R, 32, 1, 4, 1, mas_kernel<R, 32, true, 4, 1> }
+#define ALB_K8(R, TF) { R, TF, 0, 8, 1, mas_kernel<R, TF, false, 8, 1> }
+#define ALB_KS8(R) { R, 32, 1, 8, 1, mas_kernel<R, 32, true, 8, 1> }
 static const KEntry g_kernels[] = {
     ALB_K(1, 32),
     ALB_K(2, 32), ALB_K(2, 16),
@@ -71,6 +72,8 @@ static const KEntry g_kernels[] = {
     ALB_K(16, 16), ALB_K(16, 8),
     ALB_K8(8, 32), ALB_K8(8, 16), ALB_K8(8, 8),      // more than 4 compute warps: t_x > 1024
     ALB_K8(16, 16), ALB_K8(16, 8),
+    ALB_KS(1), ALB_KS(2), ALB_KS(3), ALB_KS(4), ALB_KS(6), ALB_KS(8),     // skewed: 32-frame tiles only
+    ALB_KS8(1), ALB_KS8(2), ALB_KS8(3), ALB_KS8(4), ALB_KS8(8),
 };
 static KernelFn find_kernel(int R, int TF, int skew, int nw, int minb)
 {
@@ -92,7 +95,7 @@ struct Config {
 //   throughput regime (b > #SM): 4 rows per lane, and the smallest ring (>= 2 stages) that lets the 128-register
 //                    instances reach their register-limited occupancy (8 / compute-warps CTAs per SM), so that about 8
 //                    compute warps per SM hide each other's latency and one item's backtrack overlaps others' streaming.
-static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool want_dur, Config* c)
+static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, Config* c)
 {
     const bool latency = b <= di.sms;
     int R, NW;
@@ -118,27 +121,35 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
             R = fr; NW = (tx + 32 * R - 1) / (32 * R);
         }
     }
-    if (NW > (R >= 8 ? kMaxWarps : 4))
+    if (NW > kMaxWarps)
         return fail(ALB200_E_UNSUPPORTED, "t_x=%s%lld needs too many compute warps at %lld rows per lane", "", tx, R);
     const int nblk = (ty + 31) / 32;
     const int per_sm = di.smem_optin + 1024;                   // 228 KB on sm_100
     const int tfs[3] = { R >= 16 ? 16 : 32, R == 1 ? 32 : 16, R >= 8 ? 8 : (R == 1 ? 32 : 16) };
     int best_tf = 0, best_ns = 0, best_bits = 0;
+    // skewed (systolic) forward: lane l runs one frame behind lane l-1, so the neighbour exchange leaves the per-frame
+    // dependency chain; costs 31 frames of fill per warp and 32 more per warp hand-off.  32-frame tiles only.
+    int want_skew = f_skew >= 0 ? f_skew : ((latency && NW == 1) ? 1 : 0);
+    if (!aligned || R > 8) want_skew = 0;                      // its tiles come in by TMA: 16-byte aligned rows, <= 256 rows per box
     auto try_fit = [&](int tf, int ns, int bs, int budget) -> bool {
+        if (want_skew && tf != 32) return false;
         if (f_tf && tf != f_tf) return false;
         if (f_ns && ns != f_ns) return false;
         if (f_bits >= 0 && bs != f_bits) return false;
-        const SmemLayout L = make_layout(NW, ns, R, tf, bs, nblk, want_dur);
+        const SmemLayout L = make_layout(NW, ns, R, tf, bs, nblk, want_dur, want_skew);
         if ((int64_t)L.total > budget) return false;
         best_tf = tf; best_ns = ns; best_bits = bs;
         return true;
     };
     if (latency) {
         // deepest ring that fits one CTA per SM, bits in shared memory when possible
-        for (int pass = 0; pass < 2 && !best_tf; ++pass)
+        for (int pass = 0; pass < 4 && !best_tf; ++pass) {
+            if (pass == 2) { if (f_skew >= 0 || !want_skew) break; want_skew = 0; }    // does not fit skewed: lock-step
+            const int p2 = pass & 1;
             for (int ti = 0; ti < 3 && !best_tf; ++ti)
                 for (int bs = 1; bs >= 0 && !best_tf; --bs)
-                    for (int ns = 8; ns >= (pass == 0 ? 3 : 2) && !best_tf; --ns) try_fit(tfs[ti], ns, bs, di.smem_optin);
+                    for (int ns = 8; ns >= (p2 == 0 ? 3 : 2) && !best_tf; --ns) try_fit(tfs[ti], ns, bs, di.smem_optin);
+        }
     } else {
         const int reg_occ = NW <= 4 ? 8 / (NW == 3 ? 4 : NW) : 1;          // 128-register instances: 512 compute+loader threads... 8/NW CTAs
         for (int occ = reg_occ; occ >= 1 && !best_tf; --occ) {
@@ -151,16 +162,14 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     if (!best_tf)
         return fail(ALB200_E_UNSUPPORTED, "t_x=%s%lld does not fit the shared-memory ring (max about 3300)", "", tx);
     c->R = R; c->TF = best_tf; c->NW = NW; c->NS = best_ns; c->bits_smem = best_bits;
-    // skewed (systolic) forward: the shuffle leaves the per-frame chain, but every lane adds 4 frames of pipeline fill
-    // and every warp hand-off another 124, so it only pays when one compute warp covers the whole text axis.
-    c->skew = f_skew >= 0 ? f_skew : ((latency && NW == 1) ? 1 : 0);
+    c->skew = want_skew;
     c->fn = nullptr;
     if (!latency && !c->skew)
         for (const KEntry& k : g_kernels)
             if (k.R == R && k.TF == best_tf && k.skew == 0 && NW <= k.nwmax && k.minb == 2) { c->fn = k.fn; break; }
     if (!c->fn) c->fn = find_kernel(R, best_tf, c->skew, NW, 1);
     if (!c->fn) return fail(ALB200_E_UNSUPPORTED, "no kernel instance for R=%s%lld TF=%lld", "", R, best_tf);
-    SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur);
+    SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur, want_skew);
     c->smem = L.total;
     c->bits_slot_words = (int64_t)nblk * NW * 32 * R;
     ALB_CUDA(cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));   // once per instance, never lowered
@@ -173,22 +182,22 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
 }
 
 // select_config_uncached costs a few driver calls; remember the answers (per thread, tiny table).
-struct CfgKey { int dev, latency, tx, ty, dur; char env[48]; };
-static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur, Config* c)
+struct CfgKey { int dev, latency, tx, ty, dur, aligned; char env[48]; };
+static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, Config* c)
 {
     static thread_local CfgKey keys[8];
     static thread_local Config vals[8];
     static thread_local int used = 0, next = 0;
     CfgKey k;
     memset(&k, 0, sizeof(k));
-    k.dev = di.dev; k.latency = b <= di.sms; k.tx = tx; k.ty = ty; k.dur = want_dur;
+    k.dev = di.dev; k.latency = b <= di.sms; k.tx = tx; k.ty = ty; k.dur = want_dur; k.aligned = aligned;
     if (const char* f = getenv("ALB200_FORCE")) strncpy(k.env, f, sizeof(k.env) - 1);
     int hit = -1;
     for (int i = 0; i < used; ++i)
         if (memcmp(&keys[i], &k, sizeof(k)) == 0) { hit = i; break; }
     if (hit < 0) {
         Config fresh;
-        int rc = select_config_uncached(di, b, tx, ty, want_dur, &fresh);
+        int rc = select_config_uncached(di, b, tx, ty, want_dur, aligned, &fresh);
         if (rc) return rc;
         hit = next; next = (next + 1) % 8; if (used < 8) ++used;
         keys[hit] = k; vals[hit] = fresh;
@@ -196,6 +205,42 @@ static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur
     *c = vals[hit];
     int64_t g = (int64_t)di.sms * c->occ;
     c->grid = (int)(b < g ? b : g);
+    return 0;
+}
+
+// Tensor map over values viewed as [b * t_x rows, t_y frames] fp32 with a (box_rows x box_frames) box; the skewed form's
+// loader fetches one box per tile (cp.async.bulk.tensor).  Encoding is host-side arithmetic; the last few are remembered.
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int values_tensor_map(const float* values, int b, int tx, int ty, int box_rows, int box_frames, CUtensorMap* out)
+{
+    static TmapEncodeFn enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        ALB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(ALB200_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver%s", "");
+        enc = reinterpret_cast<TmapEncodeFn>(fn);
+    }
+    struct Key { const float* v; int b, tx, ty, br, bf; };
+    static thread_local Key keys[16];
+    static thread_local CUtensorMap maps[16];
+    static thread_local int used = 0, next = 0;
+    const Key k = { values, b, tx, ty, box_rows, box_frames };
+    for (int i = 0; i < used; ++i)
+        if (keys[i].v == k.v && keys[i].b == b && keys[i].tx == tx && keys[i].ty == ty && keys[i].br == box_rows && keys[i].bf == box_frames) {
+            *out = maps[i];
+            return 0;
+        }
+    if ((int64_t)b * tx > 0x7fffffffLL) return fail(ALB200_E_UNSUPPORTED, "b * t_x = %s%lld rows exceed the tensor-map coordinate range", "", (long long)b * tx);
+    cuuint64_t dims[2] = { (cuuint64_t)ty, (cuuint64_t)b * (cuuint64_t)tx };
+    cuuint64_t strides[1] = { (cuuint64_t)ty * 4 };
+    cuuint32_t box[2] = { (cuuint32_t)box_frames, (cuuint32_t)box_rows }, es[2] = { 1, 1 };
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(values), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ALB200_E_CUDA, "cuTensorMapEncodeTiled failed with %s%lld", "", (long long)r);
+    keys[next] = k; maps[next] = *out;
+    next = (next + 1) % 16; if (used < 16) ++used;
     return 0;
 }
 
@@ -220,7 +265,9 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
     int rc = device_info(&di);
     if (rc) return rc;
     Config c;
-    rc = select_config(di, b, tx, ty, durations != nullptr, &c);
+    bool aligned = (reinterpret_cast<uintptr_t>(values) & 15) == 0 && (ty & 3) == 0;
+    if (getenv("ALB200_FORCE_UNALIGNED")) aligned = false;
+    rc = select_config(di, b, tx, ty, durations != nullptr, aligned, &c);
     if (rc) return rc;
     if (workspace_bytes < ws_bytes_for(c))
         return fail(ALB200_E_INVALID, "workspace too small: %s%lld < %lld bytes", "", (long long)workspace_bytes, (long long)ws_bytes_for(c));
@@ -235,23 +282,28 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
     p.B = b; p.Tx = tx; p.Ty = ty; p.esize = esize; p.zero_fill = zero_fill;
     p.nw = c.NW; p.ns = c.NS; p.nblk = (ty + 31) / 32;
     {
-        const SmemLayout L = make_layout(c.NW, c.NS, c.R, c.TF, c.bits_smem, p.nblk, durations != nullptr);
+        const SmemLayout L = make_layout(c.NW, c.NS, c.R, c.TF, c.bits_smem, p.nblk, durations != nullptr, c.skew);
         p.off_full = L.off_full; p.off_empty = L.off_empty; p.off_flags = L.off_flags; p.off_misc = L.off_misc; p.off_bnd = L.off_bnd;
         p.off_zero = L.off_zero; p.off_ring = L.off_ring; p.off_bits = L.off_bits; p.off_dur = L.off_dur; p.off_bt = L.off_bt; p.stage_bytes = L.stage_bytes;
     }
-    p.aligned = ((reinterpret_cast<uintptr_t>(values) & 15) == 0 && (ty & 3) == 0) ? 1 : 0;
-    if (getenv("ALB200_FORCE_UNALIGNED")) p.aligned = 0;
+    p.aligned = aligned ? 1 : 0;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (c.skew) {
+        rc = values_tensor_map(values, b, tx, ty, 32 * c.R, c.TF, &tmap);
+        if (rc) return rc;
+    }
     p.neg = neg;
     static long long* d_dbg = nullptr;
     const bool dbg = getenv("ALB200_DBG") != nullptr;
-    const size_t dbg_n = (size_t)c.grid * ((2 * kMaxWarps + 2) * 2 + kMaxWarps * 4);
+    const size_t dbg_n = (size_t)c.grid * ((2 * kMaxWarps + 2) * 2 + kMaxWarps * 8);
     if (dbg) {   // developer aid: per-warp clock64 stamps of the first item of every CTA, printed to stderr
         if (d_dbg) cudaFree(d_dbg);
         ALB_CUDA(cudaMalloc(&d_dbg, dbg_n * 8));
         ALB_CUDA(cudaMemset(d_dbg, 0, dbg_n * 8));
         p.dbg = d_dbg;
     }
-    void* args[] = { &p };
+    void* args[] = { &p, &tmap };
     ALB_CUDA(cudaLaunchKernel((const void*)c.fn, dim3(c.grid), dim3(2 * c.NW * 32), args, c.smem, stream));
     ++g_launches;
     if (dbg) {
@@ -273,6 +325,12 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
                 if (e[3] > 0)
                     fprintf(stderr, "[alb200 dbg]   w%d: %lld units; per unit: wait-full %lld, polls %lld, compute %lld, other %lld cycles\n", w, e[3],
                             e[0] / e[3], e[1] / e[3], e[2] / e[3], ((d[w * 2 + 1] - d[w * 2]) - e[0] - e[1] - e[2]) / e[3]);
+            }
+            for (int w = 0; w < c.NW; ++w) {
+                long long* e = h + (size_t)c.grid * ((2 * kMaxWarps + 2) * 2 + kMaxWarps * 4) + ((size_t)cta * kMaxWarps + w) * 4;
+                if (e[3] > 0)
+                    fprintf(stderr, "[alb200 dbg]   ld%d: %lld tiles; per tile: wait-empty %lld, issue copies %lld, zero fill %lld cycles\n", w, e[3],
+                            e[0] / e[3], e[1] / e[3], e[2] / e[3]);
             }
         }
         free(h);
@@ -351,9 +409,9 @@ size_t alb200_mas_workspace_bytes(int b, int tx, int ty)
     DevInfo di;
     if (b <= 0 || tx <= 0 || ty <= 0 || device_info(&di)) return sizeof(WsHeader);
     size_t need = sizeof(WsHeader);
-    for (int dur = 0; dur < 2; ++dur) {
+    for (int v = 0; v < 4; ++v) {
         Config c;
-        if (select_config(di, b, tx, ty, dur != 0, &c) == 0) need = std::max(need, ws_bytes_for(c));
+        if (select_config(di, b, tx, ty, (v & 1) != 0, (v & 2) != 0, &c) == 0) need = std::max(need, ws_bytes_for(c));
     }
     return need;
 }
@@ -364,7 +422,7 @@ int alb200_mas_describe(int b, int tx, int ty, int want_durations, char* buf, si
     int rc = device_info(&di);
     if (rc) return rc;
     Config c;
-    rc = select_config(di, b, tx, ty, want_durations != 0, &c);
+    rc = select_config(di, b, tx, ty, want_durations != 0, (ty & 3) == 0, &c);
     if (rc) return rc;
     if (buf && buf_bytes)
         snprintf(buf, buf_bytes, "rows_per_lane=%d tile_frames=%d warps=%d stages=%d bits=%s form=%s smem=%u grid=%d ctas_per_sm=%d",

@@ -44,6 +44,7 @@
 //     word of row (tok - l); the words are broadcast and every lane replays the
 //     walk row by row with find-leading-one (one short chain per step down).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -54,7 +55,7 @@ constexpr int kMaxWarps = 8;       // compute warps per CTA (an equal number of 
 constexpr int kRing = 128;         // frames in a warp-boundary ring
 constexpr int kZeroChunk = 7680;   // bytes per zero-fill bulk store (60 x 128; sized so 2 CTAs x 3 stages still fit an SM at t_x = 400)
 constexpr int kLanePad = 16;       // bytes of skew per lane inside a tile stage
-constexpr int kSkewLag = 4;        // frames lane l trails lane l-1 in the skewed form
+constexpr int kSkewLag = 1;        // frames lane l trails lane l-1 in the skewed form
 constexpr int kProgDone = 0x3fffffff;
 
 struct WsHeader {       // first 64 bytes of the workspace
@@ -98,11 +99,12 @@ struct SmemLayout {
 
 __host__ __device__ inline uint32_t alb_align(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF, int bits_smem, int nblk, int want_dur)
+// dense: the stages are written by 2-D TMA box loads (skewed form): rows back to back, no per-lane skew
+__host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF, int bits_smem, int nblk, int want_dur, int dense = 0)
 {
     SmemLayout L;
     const uint32_t RW = 32u * R;
-    L.stage_bytes = RW * TF * 4 + 32 * kLanePad;
+    L.stage_bytes = RW * TF * 4 + (dense ? 0 : 32 * kLanePad);
     uint32_t o = 0;
     L.off_full = o;  o += NW * NS * 8;
     L.off_empty = o; o += NW * NS * 8;
@@ -147,6 +149,14 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 // the mbarrier receives one arrival when all of this thread's earlier cp.async have landed
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 2-D TMA box load (SASS UTMALDG): rows [c1, c1+box_rows) x frames [c0, c0+box_frames) land densely at dst, bytes complete on bar
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 // shared -> global bulk store (TMA engine, UBLKCP)
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
@@ -244,34 +254,53 @@ template <int R>
 struct Fwd {
     float old[R];        // running column: value of each of our rows at the previous frame
     uint32_t wbits[R];   // direction word per row, shifted in from the top 4 frames at a time
+    uint32_t wprev[R];   // skewed: the 32 frames before those in wbits (a lane's words straddle two units)
     float up;            // lock-step: neighbour's last row at the previous frame
-    float upn[4];        // skewed: neighbour values for the four frames of the NEXT group
-    float lastp;         // skewed: our own last-row value of the previous frame (what the next shuffle ships)
+    float u1, u2;        // skewed: neighbour's last row for the next frame and the one after (shuffles two frames in flight)
     float bprev;         // lane 0: value of the row above our first row at the frame before this group
+    float bprev1;        // skewed, lane 0: ... and at the first frame of this group (the boundary ring is step-indexed)
 };
 
 // UNIT consecutive frames for this lane's R rows.
-//   Y   frame of lane 0 at the start of the unit;  yl = this lane's frame (Y, or Y - 4*lane when skewed)
+//   Y   frame of lane 0 at the start of the unit;  yl = this lane's frame (Y, or Y - lane when skewed)
 //   Reference semantics per cell: core.pyx:19-30 (see inline notes).
 // Scheduling notes (one warp per scheduler: every exposed latency is paid in full):
 //   * the tile values of group g+1 and all boundary values of the unit are fetched before they are needed;
 //   * the body is branch-free: a completed direction word is snapshotted with predicated moves and stored once,
 //     after the unit, so the four groups stay one basic block.
 template <int R, int TF, int UNIT, bool SKEW, bool DIAG>
-__device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint32_t bin_addr, uint32_t bout_addr, int Y, int yl,
+__device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint32_t tile_prev, uint32_t bin_addr, uint32_t bout_addr, int Y, int yl,
                                              bool has_in, bool lane0, bool lane31, float neg, int dxy, uint32_t* bits_row, int TXS,
                                              int y_lo, unsigned span)
 {
     constexpr int NG = UNIT / 4;
+    static_assert(!SKEW || UNIT == 32, "the skewed form assembles one direction word per 32-frame unit");
+    // Skewed form: lane l is l frames behind lane 0, so lane 31 of the warp above us finishes frame f at ITS step f + 31.  The
+    // boundary ring is indexed by the producer's step (aligned 128-bit stores); frame f sits in slot f + 31.
     float4 bin[NG];
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         bin[g] = make_float4(neg, neg, neg, neg);                    // x == 0, y > 0: v_prev = max_neg_val (core.pyx:27)
-        if (has_in) bin[g] = lds128(bin_addr + (((Y + 4 * g) & (kRing - 1)) << 2));
+        if (has_in) bin[g] = lds128(bin_addr + (((Y + 4 * g + (SKEW ? 32 : 0)) & (kRing - 1)) << 2));
     }
     float4 vn[R];
+    // Skewed form: the tiles in shared memory are NOT skewed (same 128-bit asynchronous copies as the lock-step form); lane l
+    // reads frame Y + k - l, which is tile position k - l of this tile, or 32 + k - l of the previous one while k < l.  One
+    // compare + select per frame picks the base; the loads are scalar and run two frames ahead.
+    const int lane = Y - yl;
+    const uint32_t curA = tile_addr - 4u * (uint32_t)lane, prevA = tile_prev + 4u * (uint32_t)(TF - lane);
+    float vq[2][R];
+    if (SKEW) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) vn[r] = lds128(tile_addr + r * (TF * 4));
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t a = (lane <= q) ? curA : prevA;
+#pragma unroll
+            for (int r = 0; r < R; ++r) vq[q][r] = lds32(a + q * 4 + r * (TF * 4));
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) vn[r] = lds128(tile_addr + r * (TF * 4));
+    }
     uint32_t wdone[R];                                                // the word this lane completes inside this unit, if any
 #pragma unroll
     for (int r = 0; r < R; ++r) wdone[r] = 0u;
@@ -279,14 +308,18 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         float4 v[R];
+        if (!SKEW) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = vn[r];
-        if (g + 1 < NG) {
+            for (int r = 0; r < R; ++r) v[r] = vn[r];
+            if (g + 1 < NG) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) vn[r] = lds128(tile_addr + r * (TF * 4) + (g + 1) * 16);
+                for (int r = 0; r < R; ++r) vn[r] = lds128(tile_addr + r * (TF * 4) + (g + 1) * 16);
+            }
         }
-        const float b0 = S.bprev, b1 = bin[g].x, b2 = bin[g].y, b3 = bin[g].z;   // row above us at frames Y+4g-1 .. Y+4g+2
-        S.bprev = bin[g].w;
+        // row above us at frames Y+4g-1 .. Y+4g+2 (skewed: slots Y+4g+30 .. Y+4g+33, i.e. .zw of the previous load, .xy of this one)
+        const float b0 = S.bprev, b1 = SKEW ? S.bprev1 : bin[g].x, b2 = SKEW ? bin[g].x : bin[g].y, b3 = SKEW ? bin[g].y : bin[g].z;
+        S.bprev = SKEW ? bin[g].z : bin[g].w;
+        if (SKEW) S.bprev1 = bin[g].w;
         uint32_t hb[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) hb[r] = 0u;
@@ -295,41 +328,60 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
         for (int k = 0; k < 4; ++k) {
             const int kk = 4 * g + k;
             const float bk = (k == 0) ? b0 : (k == 1) ? b1 : (k == 2) ? b2 : b3;
-            const float upv = lane0 ? bk : (SKEW ? S.upn[k] : S.up);
+            const float upv = lane0 ? bk : (SKEW ? S.u1 : S.up);
             float nv[R];
 #pragma unroll
             for (int r = R - 1; r >= 0; --r) {
                 const float stay = S.old[r];                        // v_cur  (core.pyx:22; == neg on the diagonal, rows above it are held)
                 const float move = (r == 0) ? upv : S.old[r - 1];   // v_prev (core.pyx:29)
                 const bool take = move > stay;                      // core.c:19384
-                const float vr = (k == 0) ? v[r].x : (k == 1) ? v[r].y : (k == 2) ? v[r].z : v[r].w;
+                const float vr = SKEW ? vq[kk & 1][r] : ((k == 0) ? v[r].x : (k == 1) ? v[r].y : (k == 2) ? v[r].z : v[r].w);
                 float res = (take ? move : stay) + vr;              // core.pyx:30
                 if (DIAG) res = (dxy + r > kk) ? neg : res;         // rows above the diagonal stay at the sentinel
                 nv[r] = res;
                 if (take) hb[r] |= (1u << k);
             }
             if (SKEW) {
-                S.upn[k] = __shfl_up_sync(0xffffffffu, S.lastp, 1);   // consumed at frame k of the next group
-                S.lastp = nv[R - 1];
+                // lane l-1 is one frame ahead: what it finishes now is what we need the frame after next
+                S.u1 = S.u2;
+                S.u2 = __shfl_up_sync(0xffffffffu, nv[R - 1], 1);
             } else {
                 S.up = __shfl_up_sync(0xffffffffu, nv[R - 1], 1);
             }
             o4[k] = nv[R - 1];
 #pragma unroll
             for (int r = 0; r < R; ++r) S.old[r] = nv[r];
+            if (SKEW && kk + 2 < UNIT) {
+                const uint32_t a = (lane <= kk + 2) ? curA : prevA;
+#pragma unroll
+                for (int r = 0; r < R; ++r) vq[kk & 1][r] = lds32(a + (kk + 2) * 4 + r * (TF * 4));
+            }
         }
-        if (lane31) sts128(bout_addr + (((yl + 4 * g) & (kRing - 1)) << 2), o4[0], o4[1], o4[2], o4[3]);
+        if (lane31) sts128(bout_addr + (((Y + 4 * g) & (kRing - 1)) << 2), o4[0], o4[1], o4[2], o4[3]);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             S.wbits[r] = __funnelshift_r(S.wbits[r], hb[r], 4);
-            wdone[r] = (gdone == g) ? S.wbits[r] : wdone[r];
+            if (!SKEW) wdone[r] = (gdone == g) ? S.wbits[r] : wdone[r];
         }
     }
-    const int yw = yl + 4 * gdone;                                   // first frame of the last group of the completed word
-    if (gdone < NG && (unsigned)(yw - y_lo) < span) {
-        uint32_t* brow = bits_row + (int64_t)(yw >> 5) * TXS;
+    if (SKEW) {
+        // wbits now holds our frames [Y - lane, Y + 32 - lane), wprev the 32 before: the aligned word of block [Y - 32, Y)
+        // is the 64-bit window shifted right by `lane`
+        const int yw = Y - 32;
+        if ((unsigned)(yw - y_lo) < span) {
+            uint32_t* brow = bits_row + (int64_t)(yw >> 5) * TXS;
 #pragma unroll
-        for (int r = 0; r < R; ++r) brow[r] = wdone[r];
+            for (int r = 0; r < R; ++r) brow[r] = __funnelshift_r(S.wprev[r], S.wbits[r], lane);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) S.wprev[r] = S.wbits[r];
+    } else {
+        const int yw = yl + 4 * gdone;                               // first frame of the last group of the completed word
+        if (gdone < NG && (unsigned)(yw - y_lo) < span) {
+            uint32_t* brow = bits_row + (int64_t)(yw >> 5) * TXS;
+#pragma unroll
+            for (int r = 0; r < R; ++r) brow[r] = wdone[r];
+        }
     }
 }
 
@@ -337,13 +389,13 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
 // NWMAX bounds the compute warps of an instance (4 -> 256 threads, 8 -> 512 threads).  MINB = 2 holds an instance to 128
 // registers so two CTAs share an SM (throughput regime); MINB = 1 lets an utterance that owns its SM use up to 255.
 template <int R, int TF, bool SKEW, int NWMAX, int MINB>
-__global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasParams p)
+__global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasParams p, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int RW = 32 * R;
     // hand-off granularity between warps: a whole 32-frame tile when an utterance owns its SM (fewer flag/barrier round trips per
     // frame), 16 frames in the register-capped throughput instances
     constexpr int UNIT = (MINB == 1 && TF == 32) ? 32 : (TF < 16 ? TF : 16);
-    constexpr int LANE_STRIDE = R * TF * 4 + kLanePad;
+    constexpr int LANE_STRIDE = R * TF * 4 + (SKEW ? 0 : kLanePad);   // skewed: dense TMA tiles, the scalar reads of lanes l and frames k - l hit 32 banks
     constexpr int LAG31 = SKEW ? 31 * kSkewLag : 0;      // frames lane 31 trails lane 0
 
     extern __shared__ __align__(128) unsigned char smem[];
@@ -377,7 +429,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
 
     // ---- one-time setup
     if (!is_loader && lane == 0)
-        for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, 32); mbar_init(empty0 + 8 * s, 32); }   // one arrival per lane
+        for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, SKEW ? 1 : 32); mbar_init(empty0 + 8 * s, 32); }   // one arrival per lane (full, skewed: the TMA issuer)
     for (int i = tid; i < kZeroChunk / 16; i += nthr)
         reinterpret_cast<int4*>(smem + L.off_zero)[i] = make_int4(0, 0, 0, 0);
     fence_mbar_init();
@@ -446,7 +498,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         const int y_start = x0;                                 // first frame where any of our rows is on/below the diagonal
         const int y_last = t_y - t_x + x1 - 1;                  // last frame where our last row is inside the band (core.pyx:18)
         const int span = (y_last + 1 - y_start + 31) & ~31;     // whole 32-frame direction words
-        const int y_end = y_start + span + (SKEW ? 128 : 0);    // lane-0 frames; skewed: lane 31 needs 124 more
+        const int y_end = y_start + span + (SKEW ? 32 : 0);     // lane-0 frames; skewed: lane 31 needs 31 more
         const int t_s = y_start / TF, t_e = y_end / TF;         // tiles [t_s, t_e), all whole
 
         if (is_loader) {
@@ -490,15 +542,25 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 const int my_tiles = t_e - t_s;
                 const int64_t my_chunks = (nchunks > w) ? (nchunks - w + nact - 1) / nact : 0;
                 const int zq = (int)((my_chunks + my_tiles - 1) / (my_tiles > 0 ? my_tiles : 1));
+                long long l_e = 0, l_c = 0, l_z = 0, l0 = 0, l1 = 0, l2 = 0;
                 for (int t = t_s; t < t_e; ++t) {
+                    if (dbg_on) l0 = clock64();
                     mbar_wait(empty0 + 8 * stage, phase ^ 1u);      // the compute lanes have released this stage
+                    if (dbg_on) l1 = clock64();
                     const uint32_t st = ring_a + stage * L.stage_bytes;
-                    if (p.aligned) {
+                    if (SKEW) {
+                        // one 2-D box load per tile: all 32*R rows of this warp x TF frames (the host only picks this form for
+                        // 16-byte aligned inputs); rows past t_x and frames past T_mel are fetched or zero-filled, never used
+                        if (lane == 0) {
+                            mbar_expect_tx(full0 + 8 * stage, RW * TF * 4);
+                            tma_load_2d(st, &tmap, t * TF, item * p.Tx + x0, full0 + 8 * stage);
+                        }
+                    } else if (p.aligned) {
                         // Loader lane = (16-byte chunk ck of a row, row group q0); it walks the owner lanes li = q0, q0+RPI, ...
                         // and their R rows, so one warp-wide LDGSTS.128 moves RPI whole row segments.
                         const int f0 = t * TF + ck * 4;
                         for (int li = q0; li * R < nrows; li += RPI) {
-                            const int f = SKEW ? f0 - kSkewLag * li : f0;       // frame of this chunk for owner lane li
+                            const int f = f0;                                   // frame of this chunk
                             const int lo = (x0 + li * R) & ~3;                  // chunks wholly above the diagonal are never read
                             const uint32_t d = st + li * LANE_STRIDE + ck * 16;
                             const float* src = vrow + (int64_t)(li * R) * Ty + f;
@@ -515,13 +577,19 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                         float* sp = reinterpret_cast<float*>(smem + L.off_ring + (size_t)(w * NS + stage) * L.stage_bytes);
                         for (int idx = lane; idx < nrows * TF; idx += 32) {
                             const int i = idx / TF, fl = idx - i * TF, li = i / R;
-                            const int f = t * TF + fl - (SKEW ? kSkewLag * li : 0);
+                            const int f = t * TF + fl;
                             if (f >= 0 && f <= band_hi0 + i && f < Ty) sp[(i * (TF * 4) + li * kLanePad) / 4 + fl] = vrow[(int64_t)i * Ty + f];
                         }
                         mbar_arrive(full0 + 8 * stage);
                     }
                     if (++stage == (uint32_t)NS) { stage = 0; phase ^= 1u; }
+                    if (dbg_on) l2 = clock64();
                     if (zf) issue_zero(zq);
+                    if (dbg_on) { const long long l3 = clock64(); l_e += l1 - l0; l_c += l2 - l1; l_z += l3 - l2; }
+                }
+                if (dbg_on && first_item && lane == 0) {
+                    long long* e = p.dbg + (int64_t)gridDim.x * ((2 * kMaxWarps + 2) * 2 + kMaxWarps * 4) + ((int64_t)blockIdx.x * kMaxWarps + w) * 4;
+                    e[0] = l_e; e[1] = l_c; e[2] = l_z; e[3] = t_e - t_s;
                 }
             }
             if (zf && w < nact) {
@@ -544,18 +612,25 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             Fwd<R> S;
 #pragma unroll
             for (int r = 0; r < R; ++r) { S.old[r] = neg; S.wbits[r] = 0u; }
-            S.up = neg; S.lastp = neg;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) S.upn[k] = neg;
-            S.bprev = neg;
+            for (int r = 0; r < R; ++r) S.wprev[r] = 0u;
+            S.up = neg; S.u1 = neg; S.u2 = neg;
+            S.bprev = neg; S.bprev1 = neg;
             if (!has_in) {
                 S.bprev = 0.f;                                      // x == 0, y == 0: v_prev = 0 (core.pyx:25)
             } else {
-                while (ld_flag(in_tail) < y_start + UNIT) { }
-                S.bprev = lds32(bin_addr + (((y_start - 4) & (kRing - 1)) << 2) + 12);   // V[x0-1, x0-1], the diagonal cell above us
+                while (ld_flag(in_tail) < y_start + UNIT + (SKEW ? 32 : 0)) { }
+                if (SKEW) {
+                    const float4 b = lds128(bin_addr + (((y_start + 28) & (kRing - 1)) << 2));   // frames y_start-4 .. y_start-1 (+31)
+                    S.bprev = b.z; S.bprev1 = b.w;
+                } else {
+                    S.bprev = lds32(bin_addr + (((y_start - 4) & (kRing - 1)) << 2) + 12);   // V[x0-1, x0-1], the diagonal cell above us
+                }
             }
             int seen_cons = 0;
-            int seen_in = has_in ? y_start + UNIT : kProgDone;   // producer progress as last read (prefetched one unit ahead)
+            uint32_t prev_stage = 0;
+            constexpr int IN_LEAD = SKEW ? 32 : 0;             // skewed: the producer's lane 31 trails its lane 0 by 31 steps
+            int seen_in = has_in ? y_start + UNIT + IN_LEAD : kProgDone;   // producer progress (in its steps) as last read
             uint32_t* bits_row = bits + xl0;
             long long c_full = 0, c_poll = 0, c_unit = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;   // ALB200_DBG cycle breakdown
 
@@ -564,30 +639,37 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 if (dbg_on) c0 = clock64();
                 if (fin == 0) mbar_wait(full0 + 8 * stage, phase);
                 if (dbg_on) c1 = clock64();
-                while (seen_in < y + UNIT) seen_in = ld_flag(in_tail);
+                while (seen_in < y + UNIT + IN_LEAD) seen_in = ld_flag(in_tail);
                 if (has_consumer) {
-                    const int need = y - LAG31 + UNIT - (kRing - 4);   // our lane 31 is about to overwrite these ring slots
+                    const int need = SKEW ? y + UNIT - 32 - kRing : y + UNIT - (kRing - 4);   // our lane 31 is about to overwrite these ring slots
                     while (seen_cons < need) seen_cons = ld_flag(out_head);
                 }
                 const int next_in = has_in ? ld_flag(in_tail) : kProgDone;   // read now, needed after this unit: latency hidden
                 if (dbg_on) c2 = clock64();
                 const uint32_t tile_addr = ring_a + stage * L.stage_bytes + lane * LANE_STRIDE + fin * 4;
+                const uint32_t tile_prev = (SKEW && y > y_start) ? ring_a + prev_stage * L.stage_bytes + lane * LANE_STRIDE : tile_addr;
                 const int yl = y - lag;
                 if (y < diag_end)
-                    forward_unit<R, TF, UNIT, SKEW, true>(S, tile_addr, bin_addr, bout_addr, y, yl, has_in, lane0, lane31, neg, xl0 - yl,
-                                                          bits_row, TXS, y_start, (unsigned)span);
+                    forward_unit<R, TF, UNIT, SKEW, true>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, has_in, lane0, lane31, neg,
+                                                          xl0 - yl, bits_row, TXS, y_start, (unsigned)span);
                 else
-                    forward_unit<R, TF, UNIT, SKEW, false>(S, tile_addr, bin_addr, bout_addr, y, yl, has_in, lane0, lane31, neg, 0,
-                                                           bits_row, TXS, y_start, (unsigned)span);
+                    forward_unit<R, TF, UNIT, SKEW, false>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, has_in, lane0, lane31, neg,
+                                                           0, bits_row, TXS, y_start, (unsigned)span);
                 seen_in = next_in;
                 if (dbg_on) { c3 = clock64(); c_full += c1 - c0; c_poll += c2 - c1; c_unit += c3 - c2; }
-                if (lane31) st_flag(my_tail, y + UNIT - LAG31);
+                if (lane31) st_flag(my_tail, y + UNIT);
                 if (lane0) st_flag(my_head, y + UNIT);
                 if (((y + UNIT) & (TF - 1)) == 0) {                 // tile consumed: hand the stage back to the loader
-                    mbar_arrive(empty0 + 8 * stage);
+                    if (SKEW) {                                     // the trailing lanes still read this tile during the next unit
+                        if (y > y_start) mbar_arrive(empty0 + 8 * prev_stage);
+                        prev_stage = stage;
+                    } else {
+                        mbar_arrive(empty0 + 8 * stage);
+                    }
                     if (++stage == (uint32_t)NS) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (SKEW && y_end > y_start) mbar_arrive(empty0 + 8 * prev_stage);
             if (lane31) st_flag(my_tail, kProgDone);
             if (dbg_on && first_item && lane == 0) {
                 long long* e = p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + w) * 4;

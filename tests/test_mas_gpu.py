@@ -61,8 +61,8 @@ def test_golden_vectors_through_public_api(ma, golden):
 
 # ------------------------------------------------------------------ differential, small shapes, every kernel shape
 # "rows_per_lane,tile_frames,stages,bits_in_smem,skewed" -- every kernel shape in both forward forms
-FORCES = [None, "1,32,2,1,0", "1,32,3,0,1", "2,16,2,1,0", "2,32,4,0,1", "2,32,2,1,1", "3,32,3,1,0", "3,16,3,0,1", "4,16,2,1,1",
-          "4,32,2,1,0", "6,16,2,0,0", "6,32,2,1,1", "8,32,2,1,1", "8,16,2,0,0", "8,8,3,0,1", "16,16,2,0,0", "16,8,2,0,1"]
+FORCES = [None, "1,32,2,1,0", "1,32,3,0,1", "2,16,2,1,0", "2,32,4,0,1", "2,32,2,1,1", "3,32,3,1,0", "3,32,3,0,1", "3,16,3,0,0", "4,32,2,1,1",
+          "4,16,2,1,0", "4,32,2,1,0", "6,16,2,0,0", "6,32,2,1,1", "8,32,2,1,1", "8,16,2,0,0", "8,8,3,0,0", "16,16,2,0,0", "16,8,2,0,0"]
 
 
 @pytest.mark.parametrize("force", FORCES)
