@@ -318,7 +318,7 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
             fprintf(stderr, " | item done @%lld\n", d[2 * kMaxWarps * 2 + 1] - t0);
             {
                 long long* e = h + (size_t)c.grid * (2 * kMaxWarps + 2) * 2 + ((size_t)cta * kMaxWarps + (kMaxWarps - 1)) * 4;
-                if (e[3] < 0) fprintf(stderr, "[alb200 dbg]   backtrack: %lld blocks; per block: select+fixups %lld, walk %lld, publish %lld cycles\n", -e[3], e[0], e[1], e[2]);
+                if (e[3] < 0) fprintf(stderr, "[alb200 dbg]   backtrack: %lld blocks; per block: windows+walk %lld, publish %lld cycles\n", -e[3], e[1], e[2]);
             }
             for (int w = 0; w < c.NW && w < kMaxWarps - 1; ++w) {
                 long long* e = h + (size_t)c.grid * (2 * kMaxWarps + 2) * 2 + ((size_t)cta * kMaxWarps + w) * 4;

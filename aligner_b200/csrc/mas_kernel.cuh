@@ -53,7 +53,7 @@ namespace alb {
 
 constexpr int kMaxWarps = 8;       // compute warps per CTA (an equal number of loader warps rides along)
 constexpr int kRing = 128;         // frames in a warp-boundary ring
-constexpr int kZeroChunk = 7680;   // bytes per zero-fill bulk store (60 x 128; sized so 2 CTAs x 3 stages still fit an SM at t_x = 400)
+constexpr int kZeroChunk = 7168;   // bytes per zero-fill bulk store (56 x 128; sized so 2 CTAs x 3 stages still fit an SM at t_x = 400)
 constexpr int kLanePad = 16;       // bytes of skew per lane inside a tile stage
 constexpr int kSkewLag = 1;        // frames lane l trails lane l-1 in the skewed form
 constexpr int kProgDone = 0x3fffffff;
@@ -110,7 +110,7 @@ __host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF,
     L.off_empty = o; o += NW * NS * 8;
     L.off_flags = alb_align(o, 16); o = L.off_flags + 2 * NW * 4;          // tail (lane 31) and head (lane 0) progress per warp
     L.off_misc = alb_align(o, 16);  o = L.off_misc + 64 + 2 * kMaxWarps * 16; // item/lengths + per-warp partial mask sums
-    L.off_bnd = alb_align(o, 16);   o = L.off_bnd + NW * kRing * 4;
+    L.off_bnd = alb_align(o, 16);   o = L.off_bnd + (NW + 1) * kRing * 4;           // ring 0: constant sentinel (the row above token 0), ring w+1: last row of warp w
     L.off_zero = alb_align(o, 128); o = L.off_zero + kZeroChunk;
     L.off_ring = alb_align(o, 128); o = L.off_ring + NW * NS * L.stage_bytes;
     L.off_bits = alb_align(o, 16);  o = L.off_bits + (bits_smem ? (uint32_t)nblk * NW * RW * 4 : 0);
@@ -280,8 +280,7 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
     float4 bin[NG];
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-        bin[g] = make_float4(neg, neg, neg, neg);                    // x == 0, y > 0: v_prev = max_neg_val (core.pyx:27)
-        if (has_in) bin[g] = lds128(bin_addr + (((Y + 4 * g + (SKEW ? 32 : 0)) & (kRing - 1)) << 2));
+        bin[g] = lds128(bin_addr + (((Y + 4 * g + (SKEW ? 32 : 0)) & (kRing - 1)) << 2));
     }
     float4 vn[R];
     // Skewed form: the tiles in shared memory are NOT skewed (same 128-bit asynchronous copies as the lock-step form); lane l
@@ -385,6 +384,134 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
     }
 }
 
+// ------------------------------------------------------------------ backtrack walker (one warp)
+// Walks 32 frames (one direction word per row) per step and publishes (token at the block's last frame, mask of the
+// frames at which the path steps down) per block; the other warps turn those into stores.  What the reference does
+// per frame (core.pyx:32-35: index -= 1 iff index != 0 and (index == y or value[index, y-1] < value[index-1, y-1]))
+// becomes, per ROW visited: "the next step down is at the highest frame not above the current one whose bit is set".
+//   * Words are stored bit-REVERSED (frame k at bit 31-k) so that "highest frame" is "lowest set bit":
+//         t     = W & below                 remaining step candidates on this row
+//         below'= ~(t ^ (t - 1))            frames strictly before the step (0 when t == 0: the block is finished)
+//     so the next row's t is ONE add and ONE three-input logic op after this row's: t' = W' & ~(t ^ (t - 1)).
+//   * Software pipeline over blocks, so that only [window loads -> walk] is on the serial path:
+//       iteration blk, start token known:   (1) issue the direction-word loads of block blk-LD, rows anchor-0 .. anchor-32(LD+1)+1
+//                                               with anchor = the current token (the path drops at most 32 rows per block);
+//                                           (2) patch the forced diagonal steps into the words loaded LD-1 iterations ago and
+//                                               store them as the shared-memory window of block blk-1;
+//                                           (3) walk block blk through the window stored one iteration ago (broadcast loads).
+//     LD = 2 when the bits live in shared memory, 4 when they come from L2.
+template <int LD>
+__device__ __forceinline__ void backtrack_walk(const uint32_t* bits, int TXS, int t_x, int t_y, int top, int lane, uint32_t win_a,
+                                               volatile int* btTok, volatile uint32_t* btMov, uint32_t bt_cur_a, long long* dbg_e)
+{
+    constexpr int NWD = LD + 1;                              // words per lane in a window
+    constexpr uint32_t WIN_BYTES = (NWD * 32 + 16) * 4;        // plus the walk's read-ahead
+    if (top < 0) return;
+    uint32_t fifo[LD][NWD];                                  // [0] = next block to store
+    int anchor[LD];
+    auto load_win = [&](int blk, int a, uint32_t (&wv)[NWD]) {
+#pragma unroll
+        for (int j = 0; j < NWD; ++j) {
+            const int r = a - 32 * j - lane;
+            wv[j] = (blk >= 0 && r > 0) ? bits[(int64_t)blk * TXS + r] : 0u;   // row 0 can never step down (core.pyx:34 index != 0)
+        }
+    };
+    auto store_win = [&](int blk, int a, const uint32_t (&wv)[NWD]) {
+        const int yb = blk << 5;
+        const uint32_t wbuf = win_a + (uint32_t)(blk & 1) * WIN_BYTES;
+#pragma unroll
+        for (int j = 0; j < NWD; ++j) {
+            const int r = a - 32 * j - lane, d = r - yb;
+            uint32_t v = wv[j];
+            if (r > 0 && d >= 0 && d < 32) v |= (1u << d);                   // diagonal cell: forced step (index == y)
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wbuf + 4u * (uint32_t)(32 * j + lane)), "r"(__brev(v)) : "memory");
+        }
+    };
+    int tok0 = t_x - 1;
+    // prologue: blocks top .. top-LD+1 are all anchored at the final token
+    int anc_cur = tok0;
+#pragma unroll
+    for (int j = 0; j < LD; ++j) { load_win(top - j, tok0, fifo[j]); anchor[j] = tok0; }
+    store_win(top, tok0, fifo[0]);
+#pragma unroll
+    for (int j = 0; j + 1 < LD; ++j) {
+#pragma unroll
+        for (int q = 0; q < NWD; ++q) fifo[j][q] = fifo[j + 1][q];
+        anchor[j] = anchor[j + 1];
+    }
+    __syncwarp();
+    long long bB = 0, bC = 0, q0 = 0, q2 = 0;
+    for (int blk = top; blk >= 0; --blk) {
+        if (dbg_e) q0 = clock64();
+        const int yb = blk << 5;
+        const int nvalid = (t_y - yb < 32) ? t_y - yb : 32;
+        // (3a) first window words of this block: the only loads on the serial path
+        uint32_t wadr = win_a + (uint32_t)(blk & 1) * WIN_BYTES + 4u * (uint32_t)(anc_cur - tok0);
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(wadr) : "memory");      // "memory": nothing is hoisted above these
+        asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(w1) : "r"(wadr) : "memory");
+        asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(w2) : "r"(wadr) : "memory");
+        asm volatile("ld.shared.b32 %0, [%1+12];" : "=r"(w3) : "r"(wadr) : "memory");
+        // (1) loads for block blk-LD, anchored here;  (2) window of block blk-1 from the words loaded LD-1 iterations ago
+        load_win(blk - LD, tok0, fifo[LD - 1]);
+        anchor[LD - 1] = tok0;
+        const int anc_next = anchor[0];
+        // (3b) the walk.  Rows are left strictly in the order tok0, tok0-1, ...; every lane replays the same scalar walk.
+        uint32_t moves = 0u;                                                           // bit 31-k: the path steps down going from frame k to k-1
+        const uint32_t below0 = (nvalid < 32) ? ~((1u << (32 - nvalid)) - 1u) : 0xffffffffu;   // (reversed) frames of this block
+        uint32_t t = w0 & below0;
+#define ALB_BT_STEP(T_IN, W_NEXT, T_OUT)                                                                                \
+    {                                                                                                                   \
+        const uint32_t tm = (T_IN) - 1u;                                                                                \
+        moves |= (T_IN) & ~tm;                        /* the step: highest remaining frame = lowest reversed bit */     \
+        T_OUT = (W_NEXT) & ~((T_IN) ^ tm);            /* earlier frames go to the rows further down; 0 ends the block */ \
+    }
+        // branch-free steps (a GPU does not speculate: a per-step exit test would put the branch latency on the chain); once a
+        // row has no step left, t is 0 and the remaining steps of the group are no-ops.  Reads may run a few words past the
+        // window (the buffer is padded); those values meet t == 0 and are never used.  The first eight steps are straight-line
+        // code in the same basic block as (1) and (2), so the scheduler hides those in the shadow of the chain.
+#define ALB_BT_QUAD                                                                                                     \
+        {                                                                                                               \
+            uint32_t t1, t2, t3;                                                                                        \
+            asm volatile("ld.shared.b32 %0, [%1+16];" : "=r"(w0) : "r"(wadr));                                          \
+            ALB_BT_STEP(t, w1, t1)                                                                                      \
+            asm volatile("ld.shared.b32 %0, [%1+20];" : "=r"(w1) : "r"(wadr));                                          \
+            ALB_BT_STEP(t1, w2, t2)                                                                                     \
+            asm volatile("ld.shared.b32 %0, [%1+24];" : "=r"(w2) : "r"(wadr));                                          \
+            ALB_BT_STEP(t2, w3, t3)                                                                                     \
+            asm volatile("ld.shared.b32 %0, [%1+28];" : "=r"(w3) : "r"(wadr));                                          \
+            ALB_BT_STEP(t3, w0, t)                                                                                      \
+            wadr += 16u;                                                                                                \
+        }
+        ALB_BT_QUAD
+        ALB_BT_QUAD
+        // (2) in program order AFTER the straight-line steps: the stores are fire-and-forget, and the arithmetic that feeds
+        // them is free to move up into the idle issue slots of the chain above
+        store_win(blk - 1, anchor[0], fifo[0]);               // unconditional (block -1 lands in a buffer nobody reads): no branch, one basic block
+        __syncwarp();                                         // the window of block blk-1 is visible to every lane before its walk
+#pragma unroll
+        for (int j = 0; j + 1 < LD; ++j) {
+#pragma unroll
+            for (int q = 0; q < NWD; ++q) fifo[j][q] = fifo[j + 1][q];
+            anchor[j] = anchor[j + 1];
+        }
+        while (t != 0u) ALB_BT_QUAD
+#undef ALB_BT_QUAD
+#undef ALB_BT_STEP
+        const int nmove = __popc(moves);
+        if (dbg_e) q2 = clock64();
+        if (lane == 0) {
+            btTok[blk] = tok0;
+            btMov[blk] = moves;
+            st_flag(bt_cur_a, blk);                           // same lane, after the payload: in-order shared-memory pipe
+        }
+        anc_cur = anc_next;
+        tok0 -= nmove;
+        if (dbg_e) { const long long q3 = clock64(); bB += q2 - q0; bC += q3 - q2; }
+    }
+    if (dbg_e && lane == 0) { dbg_e[0] = 0; dbg_e[1] = bB / (top + 1); dbg_e[2] = bC / (top + 1); dbg_e[3] = -(top + 1); }
+}
+
 // ------------------------------------------------------------------ the kernel
 // NWMAX bounds the compute warps of an instance (4 -> 256 threads, 8 -> 512 threads).  MINB = 2 holds an instance to 128
 // registers so two CTAs share an SM (throughput regime); MINB = 1 lets an utterance that owns its SM use up to 255.
@@ -432,6 +559,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, SKEW ? 1 : 32); mbar_init(empty0 + 8 * s, 32); }   // one arrival per lane (full, skewed: the TMA issuer)
     for (int i = tid; i < kZeroChunk / 16; i += nthr)
         reinterpret_cast<int4*>(smem + L.off_zero)[i] = make_int4(0, 0, 0, 0);
+    for (int i = tid; i < kRing; i += nthr) reinterpret_cast<float*>(smem + L.off_bnd)[i] = p.neg;
     fence_mbar_init();
     fence_proxy_async_smem();
     __syncthreads();
@@ -603,8 +731,8 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             const bool lane0 = (lane == 0), lane31 = (lane == 31);
             const int xl0 = x0 + lane * R;
             const int lag = SKEW ? kSkewLag * lane : 0;
-            const uint32_t bin_addr = bnd_a + (has_in ? (w - 1) : 0) * kRing * 4;
-            const uint32_t bout_addr = bnd_a + w * kRing * 4;
+            const uint32_t bin_addr = bnd_a + w * kRing * 4;           // warp 0 reads the constant sentinel ring: x == 0, y > 0: v_prev = max_neg_val (core.pyx:27)
+            const uint32_t bout_addr = bnd_a + (w + 1) * kRing * 4;
             const uint32_t my_tail = tail_a + 4 * w, my_head = head_a + 4 * w;
             const uint32_t in_tail = tail_a + 4 * (has_in ? w - 1 : 0), out_head = head_a + 4 * (has_consumer ? w + 1 : w);
             const int diag_end = SKEW ? x0 + RW + LAG31 : x1;      // lane-0 frame from which no lane holds a row any more
@@ -627,7 +755,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                     S.bprev = lds32(bin_addr + (((y_start - 4) & (kRing - 1)) << 2) + 12);   // V[x0-1, x0-1], the diagonal cell above us
                 }
             }
-            int seen_cons = 0;
+            int seen_cons = has_consumer ? 0 : kProgDone;
             uint32_t prev_stage = 0;
             constexpr int IN_LEAD = SKEW ? 32 : 0;             // skewed: the producer's lane 31 trails its lane 0 by 31 steps
             int seen_in = has_in ? y_start + UNIT + IN_LEAD : kProgDone;   // producer progress (in its steps) as last read
@@ -640,11 +768,14 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 if (fin == 0) mbar_wait(full0 + 8 * stage, phase);
                 if (dbg_on) c1 = clock64();
                 while (seen_in < y + UNIT + IN_LEAD) seen_in = ld_flag(in_tail);
-                if (has_consumer) {
+                {
                     const int need = SKEW ? y + UNIT - 32 - kRing : y + UNIT - (kRing - 4);   // our lane 31 is about to overwrite these ring slots
                     while (seen_cons < need) seen_cons = ld_flag(out_head);
                 }
-                const int next_in = has_in ? ld_flag(in_tail) : kProgDone;   // read now, needed after this unit: latency hidden
+                // read now, needed after this unit (latency hidden): both neighbours' progress.  (Probing the next tile's barrier
+                // here with mbarrier.test_wait was measured: the probe itself costs ~800 cycles per unit -- profiles/r01_notes.md.)
+                const int next_in = has_in ? ld_flag(in_tail) : kProgDone;
+                const int next_cons = has_consumer ? ld_flag(out_head) : kProgDone;
                 if (dbg_on) c2 = clock64();
                 const uint32_t tile_addr = ring_a + stage * L.stage_bytes + lane * LANE_STRIDE + fin * 4;
                 const uint32_t tile_prev = (SKEW && y > y_start) ? ring_a + prev_stage * L.stage_bytes + lane * LANE_STRIDE : tile_addr;
@@ -656,6 +787,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                     forward_unit<R, TF, UNIT, SKEW, false>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, has_in, lane0, lane31, neg,
                                                            0, bits_row, TXS, y_start, (unsigned)span);
                 seen_in = next_in;
+                seen_cons = next_cons;
                 if (dbg_on) { c3 = clock64(); c_full += c1 - c0; c_poll += c2 - c1; c_unit += c3 - c2; }
                 if (lane31) st_flag(my_tail, y + UNIT);
                 if (lane0) st_flag(my_head, y + UNIT);
@@ -685,82 +817,11 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         // stores, so address arithmetic and memory traffic are off the serial chain.
         const int top = (t_y - 1) >> 5;
         if (wid == 0) {
-            int tok0 = t_x - 1, base = tok0;
-            // direction words of rows (base - lane) and (base - 32 - lane): the next block's window starts at most 32 rows
-            // below this one's, so both candidates are fetched a block ahead and the load latency hides behind the walk
-            auto load_pair = [&](int blk, int bs, uint32_t& a, uint32_t& b2) {
-                const int ra = bs - lane, rb = bs - 32 - lane;
-                a = (ra > 0) ? bits[(int64_t)blk * TXS + ra] : 0u;      // row 0 can never step down (core.pyx:34 index != 0)
-                b2 = (rb > 0) ? bits[(int64_t)blk * TXS + rb] : 0u;
-            };
-            uint32_t wA = 0u, wB = 0u;
-            if (top >= 0) load_pair(top, base, wA, wB);
-            long long bA = 0, bB = 0, bC = 0, q0 = 0, q1 = 0, q2 = 0;
-            for (int blk = top; blk >= 0; --blk) {
-                if (dbg_on) q0 = clock64();
-                const int yb = blk << 5;
-                const int nvalid = (t_y - yb < 32) ? t_y - yb : 32;
-                // the 64-row window goes through shared memory (warp 0's boundary ring is idle now): every lane patches the
-                // diagonal cells of its two rows (forced step, index == y) and stores them; the walk then reads consecutive words
-                const int ra = base - lane, rb = base - 32 - lane;
-                const int da = ra - yb, db = rb - yb;
-                if (ra > 0 && da >= 0 && da < 32) wA |= (1u << da);
-                if (rb > 0 && db >= 0 && db < 32) wB |= (1u << db);
-                const uint32_t wbuf = bnd_a + (uint32_t)(blk & 1) * 256;
-                __syncwarp();
-                // stored bit-REVERSED (frame k at bit 31-k): "next step at the highest frame not above the current one" becomes
-                // "lowest set bit", which is two plain ALU ops (t & -t); find-leading-one is a slow-pipe instruction
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wbuf + 4 * lane), "r"(__brev(wA)) : "memory");
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wbuf + 128 + 4 * lane), "r"(__brev(wB)) : "memory");
-                __syncwarp();
-                const int shift = base - tok0;                    // 0..32: where this block's first row sits in the window
-                if (blk > 0) load_pair(blk - 1, tok0, wA, wB);    // next block's candidates, a block ahead
-                // Rows are left strictly in the order tok0, tok0-1, ...: on row j the next step down is at the highest set bit
-                // at or below the current frame.  Every lane replays the same scalar walk on broadcast loads that run three
-                // rows ahead, so the chain per STEP is and / find-leading-one / mask.
-                uint32_t moves = 0u;                                                // bit 31-k set: the path steps down when going from frame k to k-1
-                uint32_t below = (nvalid < 32) ? ~((1u << (32 - nvalid)) - 1u) : 0xffffffffu;   // (reversed) frames not yet assigned to a row
-                int nmove = 0;
-                if (dbg_on) q1 = clock64();
-                // three broadcast loads in flight, registers rotated by unrolling (reads may run two words past the window: the
-                // boundary-ring region continues behind it, the values are never used)
-                uint32_t wadr = wbuf + 4u * (uint32_t)shift;
-                uint32_t w0, w1, w2;
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(wadr));
-                asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(w1) : "r"(wadr));
-                asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(w2) : "r"(wadr));
-#define ALB_BT_STEP(W)                                                                                                  \
-    {                                                                                                                   \
-        const uint32_t t = (W) & below;               /* 0: stays on this row down to the start of the block */         \
-        const uint32_t lsb = t & (0u - t);            /* the step: highest remaining frame = lowest reversed bit */     \
-        moves |= lsb;                                                                                                   \
-        below = ~(lsb | (lsb - 1u));                  /* earlier frames go to the rows further down; t == 0 -> 0 */     \
-        wadr += 4u;                                                                                                     \
-        asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(W) : "r"(wadr));                                                \
-    }
-                // branch-free steps (a GPU does not speculate: a per-step exit test would put the branch latency on the chain);
-                // once a row has no step left, `below` is 0 and the remaining steps of the trio are no-ops
-                do {
-                    ALB_BT_STEP(w0)
-                    ALB_BT_STEP(w1)
-                    ALB_BT_STEP(w2)
-                } while (below != 0u);
-                nmove = __popc(moves);
-#undef ALB_BT_STEP
-                if (dbg_on) q2 = clock64();
-                if (lane == 0) {
-                    btTok[blk] = tok0;
-                    btMov[blk] = moves;
-                    st_flag(bt_cur_a, blk);                       // same lane, after the payload: in-order shared-memory pipe
-                }
-                base = tok0;
-                tok0 -= nmove;
-                if (dbg_on) { const long long q3 = clock64(); bA += q1 - q0; bB += q2 - q1; bC += q3 - q2; }
-            }
-            if (dbg_on && first_item && lane == 0 && top >= 0) {
-                long long* e = p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4;
-                e[0] = bA / (top + 1); e[1] = bB / (top + 1); e[2] = bC / (top + 1); e[3] = -(top + 1);
-            }
+            if (bits_smem) backtrack_walk<2>(bits, TXS, t_x, t_y, top, lane, smem0 + L.off_ring, btTok, btMov, bt_cur_a,
+                                             dbg_on && first_item ? p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4 : nullptr);
+            else           backtrack_walk<4>(bits, TXS, t_x, t_y, top, lane, smem0 + L.off_ring, btTok, btMov, bt_cur_a,
+                                             dbg_on && first_item ? p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4 : nullptr);
+            fence_proxy_async_smem();   // the row windows went through the generic proxy into ring memory that TMA writes next
         } else {
             if (p.frame_tok != nullptr)
                 for (int yy = t_y + (tid - 32); yy < Ty; yy += nthr - 32) p.frame_tok[(int64_t)item * Ty + yy] = -1;
