@@ -128,8 +128,9 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     const int tfs[3] = { R >= 16 ? 16 : 32, R == 1 ? 32 : 16, R >= 8 ? 8 : (R == 1 ? 32 : 16) };
     int best_tf = 0, best_ns = 0, best_bits = 0;
     // skewed (systolic) forward: lane l runs one frame behind lane l-1, so the neighbour exchange leaves the per-frame
-    // dependency chain; costs 31 frames of fill per warp and 32 more per warp hand-off.  32-frame tiles only.
-    int want_skew = f_skew >= 0 ? f_skew : ((latency && NW == 1) ? 1 : 0);
+    // dependency chain; costs 31 frames of fill per warp and 32 more per warp hand-off.  32-frame tiles only.  Measured
+    // (profiles/r01_skew_sweep.json): faster or equal wherever an utterance owns its SM and has <= 4 rows per lane.
+    int want_skew = f_skew >= 0 ? f_skew : ((latency && R <= 4) ? 1 : 0);
     if (!aligned || R > 8) want_skew = 0;                      // its tiles come in by TMA: 16-byte aligned rows, <= 256 rows per box
     auto try_fit = [&](int tf, int ns, int bs, int budget) -> bool {
         if (want_skew && tf != 32) return false;

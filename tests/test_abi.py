@@ -52,7 +52,8 @@ def test_sass_uses_bulk_copy_engine(lib_path):
     """UBLKCP = cp.async.bulk (TMA engine) must be in the shipped SASS (B200_PROFILING.md)."""
     out = subprocess.run(["cuobjdump", "-sass", str(lib_path)], capture_output=True, text=True).stdout
     assert "UBLKCP" in out           # bulk shared->global zero fill
-    assert "LDGSTS.E.BYPASS.128" in out  # 128-bit async tile loads
+    assert "LDGSTS.E.BYPASS.128" in out  # 128-bit async tile loads (lock-step form)
+    assert "UTMALDG.2D" in out       # 2-D TMA box loads (skewed form)
     assert "SYNCS" in out          # mbarrier ops
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", str(lib_path)], capture_output=True, text=True).stdout
 
