@@ -10,5 +10,6 @@ Everything computes in hand-written CUDA reached through a C ABI
 """
 from . import _lib  # noqa: F401  (raises ImportError if the CUDA library is not built)
 from .monotonic_align import maximum_path, maximum_path_c, maximum_path_lengths  # noqa: F401
+from .sharding import balance_shards, lpt_order  # noqa: F401  (multi-GPU / ragged-batch planning)
 
 __version__ = "0.1.0"

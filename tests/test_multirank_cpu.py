@@ -45,6 +45,72 @@ def test_two_rank_gather_and_crosscheck(tmp_path):
     assert "MULTIRANK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+SHARD_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+import importlib.util
+spec = importlib.util.spec_from_file_location("sharding", os.path.join(%(root)r, "aligner_b200", "sharding.py"))   # no CUDA library needed
+sharding = importlib.util.module_from_spec(spec); spec.loader.exec_module(sharding)
+from oracle import mas
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(7)                      # same seed on every rank: the plan is computed locally, identically
+b, tx, ty = 24, 40, 120
+t_x = rng.integers(5, tx + 1, b).astype(np.int32)
+t_y = np.array([rng.integers(max(20, t_x[i]), ty + 1) for i in range(b)], np.int32)
+values = rng.standard_normal((b, tx, ty)).astype(np.float32)
+shards = sharding.balance_shards(t_x, t_y, world)
+mine = shards[rank]
+p = np.zeros((len(mine), tx, ty), np.int32)
+mas.maximum_path_c_port(p, values[mine].copy(), t_x[mine].copy(), t_y[mine].copy())
+dur = torch.zeros(b, tx, dtype=torch.int32)
+dur[torch.from_numpy(mine)] = torch.from_numpy(p.sum(-1).astype(np.int32))
+dist.all_reduce(dur, op=dist.ReduceOp.SUM)        # shards are disjoint: the sum assembles the whole batch
+full = np.zeros((b, tx, ty), np.int32)
+mas.maximum_path_c_port(full, values.copy(), t_x.copy(), t_y.copy())
+assert np.array_equal(dur.numpy(), full.sum(-1)), "sharded durations differ from the unsharded run"
+loads = sharding.shard_loads(t_x, t_y, shards)
+assert sorted(np.concatenate(shards).tolist()) == list(range(b))
+assert loads.max() - loads.min() <= sharding.item_cost(t_x, t_y).max()      # LPT bound
+if rank == 0: print("SHARD_OK", loads.tolist())
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_cost_balanced_shards(tmp_path):
+    script = tmp_path / "shard_worker.py"
+    script.write_text(SHARD_WORKER % {"root": str(ROOT)})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29534", str(script)], capture_output=True, text=True, timeout=240, env=env, cwd=str(ROOT))
+    assert "SHARD_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_balance_shards_properties():
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("sharding", ROOT / "aligner_b200" / "sharding.py")
+    sharding = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sharding)
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 3, 8):
+        for b in (0, 1, 5, 257):
+            t_x = rng.integers(1, 400, b)
+            t_y = t_x + rng.integers(0, 1600, b)
+            shards = sharding.balance_shards(t_x, t_y, world)
+            assert len(shards) == world
+            assert sorted(np.concatenate(shards).tolist() if b else []) == list(range(b))
+            if b:
+                loads = sharding.shard_loads(t_x, t_y, shards)
+                assert loads.max() - loads.min() <= sharding.item_cost(t_x, t_y).max()
+                for s in shards:        # descending cost inside a shard
+                    c = sharding.item_cost(t_x, t_y)[s]
+                    assert np.all(c[:-1] >= c[1:])
+    order = sharding.lpt_order([3, 9, 9, 1], [10, 10, 10, 10])
+    assert order.tolist() == [1, 2, 0, 3]
+
+
 def test_reference_arm_runs_on_cpu():
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--workload", "c1"],
                          capture_output=True, text=True, timeout=240, cwd=str(ROOT))
