@@ -83,7 +83,7 @@ static KernelFn find_kernel(int R, int TF, int skew, int nw, int minb)
 }
 
 struct Config {
-    int R, TF, NW, NS, bits_smem, skew, grid, occ;
+    int R, TF, NW, NS, bits_smem, skew, grid, occ, nc;
     uint32_t smem;
     int64_t bits_slot_words;
     KernelFn fn;
@@ -114,13 +114,23 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
         R = tx <= 64 ? 2 : (tx <= 512 ? 4 : (tx <= 2048 ? 8 : 16));
         NW = (tx + 32 * R - 1) / (32 * R);
     }
-    int f_tf = 0, f_ns = 0, f_bits = -1, f_skew = -1;
-    if (const char* f = getenv("ALB200_FORCE")) {   // "R,TF,NS,bits_smem,skew" -- tuning / tests only
-        int fr = 0;
-        if (sscanf(f, "%d,%d,%d,%d,%d", &fr, &f_tf, &f_ns, &f_bits, &f_skew) >= 1 && fr > 0) {
-            R = fr; NW = (tx + 32 * R - 1) / (32 * R);
-        }
+    int f_tf = 0, f_ns = 0, f_bits = -1, f_skew = -1, f_nc = 0;
+    int fr = 0;
+    if (const char* f = getenv("ALB200_FORCE"))    // "R,TF,NS,bits_smem,skew,cluster" -- tuning / tests only
+        sscanf(f, "%d,%d,%d,%d,%d,%d", &fr, &f_tf, &f_ns, &f_bits, &f_skew, &f_nc);
+    // Cluster mode: an utterance whose text axis needs more than 4 rows per lane in one CTA (t_x > 512) loses the fast
+    // skewed form; split its rows over the CTAs of a thread-block cluster instead (2 rows per lane, 4 compute warps per
+    // CTA, boundary rows handed over through distributed shared memory).  Only when every cluster gets its own SMs.
+    int NC = 1;
+    if (f_nc > 0) NC = f_nc;
+    else if (latency && aligned && tx > 512 && fr == 0 && f_skew != 0) {
+        const int want = (tx + 255) / 256;
+        if (want <= 8 && (int64_t)b * want <= di.sms) NC = want;
     }
+    if (NC > 1 && fr == 0) { R = 2; NW = 4; }
+    if (fr > 0) { R = fr; NW = (tx + 32 * R * NC - 1) / (32 * R * NC); }
+    if (NC > 1 && (!aligned || NC > 8 || 32 * R * NW * NC < tx))
+        return fail(ALB200_E_UNSUPPORTED, "cluster of %s%lld CTAs cannot take t_x=%lld", "", NC, tx);
     if (NW > kMaxWarps)
         return fail(ALB200_E_UNSUPPORTED, "t_x=%s%lld needs too many compute warps at %lld rows per lane", "", tx, R);
     const int nblk = (ty + 31) / 32;
@@ -131,13 +141,15 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     // dependency chain; costs 31 frames of fill per warp and 32 more per warp hand-off.  32-frame tiles only.  Measured
     // (profiles/r01_skew_sweep.json): faster or equal wherever an utterance owns its SM and has <= 4 rows per lane.
     int want_skew = f_skew >= 0 ? f_skew : ((latency && R <= 4) ? 1 : 0);
+    if (NC > 1) want_skew = 1;
     if (!aligned || R > 8) want_skew = 0;                      // its tiles come in by TMA: 16-byte aligned rows, <= 256 rows per box
     auto try_fit = [&](int tf, int ns, int bs, int budget) -> bool {
         if (want_skew && tf != 32) return false;
         if (f_tf && tf != f_tf) return false;
         if (f_ns && ns != f_ns) return false;
         if (f_bits >= 0 && bs != f_bits) return false;
-        const SmemLayout L = make_layout(NW, ns, R, tf, bs, nblk, want_dur, want_skew);
+        if (NC > 1 && bs != 0) return false;                   // the walker (CTA 0) reads every CTA's bits: L2 slot
+        const SmemLayout L = make_layout(NW, ns, R, tf, bs, nblk, want_dur, want_skew, NC);
         if ((int64_t)L.total > budget) return false;
         best_tf = tf; best_ns = ns; best_bits = bs;
         return true;
@@ -162,7 +174,7 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     }
     if (!best_tf)
         return fail(ALB200_E_UNSUPPORTED, "t_x=%s%lld does not fit the shared-memory ring (max about 3300)", "", tx);
-    c->R = R; c->TF = best_tf; c->NW = NW; c->NS = best_ns; c->bits_smem = best_bits;
+    c->R = R; c->TF = best_tf; c->NW = NW; c->NS = best_ns; c->bits_smem = best_bits; c->nc = NC;
     c->skew = want_skew;
     c->fn = nullptr;
     if (!latency && !c->skew)
@@ -170,9 +182,9 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
             if (k.R == R && k.TF == best_tf && k.skew == 0 && NW <= k.nwmax && k.minb == 2) { c->fn = k.fn; break; }
     if (!c->fn) c->fn = find_kernel(R, best_tf, c->skew, NW, 1);
     if (!c->fn) return fail(ALB200_E_UNSUPPORTED, "no kernel instance for R=%s%lld TF=%lld", "", R, best_tf);
-    SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur, want_skew);
+    SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur, want_skew, NC);
     c->smem = L.total;
-    c->bits_slot_words = (int64_t)nblk * NW * 32 * R;
+    c->bits_slot_words = (int64_t)nblk * NC * NW * 32 * R;
     ALB_CUDA(cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));   // once per instance, never lowered
     int occ = 0;
     ALB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->fn, 2 * NW * 32, c->smem));
@@ -183,7 +195,7 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
 }
 
 // select_config_uncached costs a few driver calls; remember the answers (per thread, tiny table).
-struct CfgKey { int dev, latency, tx, ty, dur, aligned; char env[48]; };
+struct CfgKey { int dev, latency, tx, ty, dur, aligned, bclass; char env[48]; };
 static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, Config* c)
 {
     static thread_local CfgKey keys[8];
@@ -192,6 +204,7 @@ static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur
     CfgKey k;
     memset(&k, 0, sizeof(k));
     k.dev = di.dev; k.latency = b <= di.sms; k.tx = tx; k.ty = ty; k.dur = want_dur; k.aligned = aligned;
+    k.bclass = (k.latency && tx > 512) ? b : 0;                 // the cluster decision depends on how many clusters fit
     if (const char* f = getenv("ALB200_FORCE")) strncpy(k.env, f, sizeof(k.env) - 1);
     int hit = -1;
     for (int i = 0; i < used; ++i)
@@ -205,7 +218,7 @@ static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur
     }
     *c = vals[hit];
     int64_t g = (int64_t)di.sms * c->occ;
-    c->grid = (int)(b < g ? b : g);
+    c->grid = c->nc > 1 ? b * c->nc : (int)(b < g ? b : g);
     return 0;
 }
 
@@ -247,7 +260,7 @@ static int values_tensor_map(const float* values, int b, int tx, int ty, int box
 
 static size_t ws_bytes_for(const Config& c)
 {
-    return sizeof(WsHeader) + (c.bits_smem ? 0 : (size_t)c.grid * c.bits_slot_words * 4);
+    return sizeof(WsHeader) + (c.bits_smem ? 0 : (size_t)(c.grid / c.nc) * c.bits_slot_words * 4);
 }
 
 static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t_ys, const void* mask, int mask_dtype,
@@ -281,9 +294,9 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
     p.bits_ws = c.bits_smem ? nullptr : reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(workspace) + sizeof(WsHeader));
     p.one = one; p.bits_slot_words = c.bits_slot_words;
     p.B = b; p.Tx = tx; p.Ty = ty; p.esize = esize; p.zero_fill = zero_fill;
-    p.nw = c.NW; p.ns = c.NS; p.nblk = (ty + 31) / 32;
+    p.nw = c.NW; p.ns = c.NS; p.nblk = (ty + 31) / 32; p.nc = c.nc;
     {
-        const SmemLayout L = make_layout(c.NW, c.NS, c.R, c.TF, c.bits_smem, p.nblk, durations != nullptr, c.skew);
+        const SmemLayout L = make_layout(c.NW, c.NS, c.R, c.TF, c.bits_smem, p.nblk, durations != nullptr, c.skew, c.nc);
         p.off_full = L.off_full; p.off_empty = L.off_empty; p.off_flags = L.off_flags; p.off_misc = L.off_misc; p.off_bnd = L.off_bnd;
         p.off_zero = L.off_zero; p.off_ring = L.off_ring; p.off_bits = L.off_bits; p.off_dur = L.off_dur; p.off_bt = L.off_bt; p.stage_bytes = L.stage_bytes;
     }
@@ -305,7 +318,18 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
         p.dbg = d_dbg;
     }
     void* args[] = { &p, &tmap };
-    ALB_CUDA(cudaLaunchKernel((const void*)c.fn, dim3(c.grid), dim3(2 * c.NW * 32), args, c.smem, stream));
+    if (c.nc > 1) {
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof(lc));
+        lc.gridDim = dim3(c.grid); lc.blockDim = dim3(2 * c.NW * 32); lc.dynamicSmemBytes = c.smem; lc.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = c.nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        ALB_CUDA(cudaLaunchKernelExC(&lc, (const void*)c.fn, args));
+    } else {
+        ALB_CUDA(cudaLaunchKernel((const void*)c.fn, dim3(c.grid), dim3(2 * c.NW * 32), args, c.smem, stream));
+    }
     ++g_launches;
     if (dbg) {
         long long* h = (long long*)malloc(dbg_n * 8);
@@ -426,8 +450,8 @@ int alb200_mas_describe(int b, int tx, int ty, int want_durations, char* buf, si
     rc = select_config(di, b, tx, ty, want_durations != 0, (ty & 3) == 0, &c);
     if (rc) return rc;
     if (buf && buf_bytes)
-        snprintf(buf, buf_bytes, "rows_per_lane=%d tile_frames=%d warps=%d stages=%d bits=%s form=%s smem=%u grid=%d ctas_per_sm=%d",
-                 c.R, c.TF, c.NW, c.NS, c.bits_smem ? "smem" : "global", c.skew ? "skewed" : "lockstep", c.smem, c.grid, c.occ);
+        snprintf(buf, buf_bytes, "rows_per_lane=%d tile_frames=%d warps=%d stages=%d bits=%s form=%s smem=%u grid=%d ctas_per_sm=%d cluster=%d",
+                 c.R, c.TF, c.NW, c.NS, c.bits_smem ? "smem" : "global", c.skew ? "skewed" : "lockstep", c.smem, c.grid, c.occ, c.nc);
     return 0;
 }
 

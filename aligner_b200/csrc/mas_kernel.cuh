@@ -88,6 +88,7 @@ struct MasParams {
     int ns;                     // ring stages per warp
     int nblk;                   // ceil(Ty/32)
     int aligned;                // values base and Ty allow 16-byte copies
+    int nc;                     // CTAs per utterance (thread-block cluster; 1 = one CTA per utterance)
     float neg;
     uint32_t off_full, off_empty, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, off_bt, stage_bytes;   // make_layout(), done on the host
 };
@@ -100,7 +101,7 @@ struct SmemLayout {
 __host__ __device__ inline uint32_t alb_align(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 // dense: the stages are written by 2-D TMA box loads (skewed form): rows back to back, no per-lane skew
-__host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF, int bits_smem, int nblk, int want_dur, int dense = 0)
+__host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF, int bits_smem, int nblk, int want_dur, int dense = 0, int nc = 1)
 {
     SmemLayout L;
     const uint32_t RW = 32u * R;
@@ -108,13 +109,13 @@ __host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF,
     uint32_t o = 0;
     L.off_full = o;  o += NW * NS * 8;
     L.off_empty = o; o += NW * NS * 8;
-    L.off_flags = alb_align(o, 16); o = L.off_flags + 2 * NW * 4;          // tail (lane 31) and head (lane 0) progress per warp
+    L.off_flags = alb_align(o, 16); o = L.off_flags + (2 * NW + 2) * 4;    // tail (lane 31) and head (lane 0) progress per warp, + the two cross-CTA slots
     L.off_misc = alb_align(o, 16);  o = L.off_misc + 64 + 2 * kMaxWarps * 16; // item/lengths + per-warp partial mask sums
     L.off_bnd = alb_align(o, 16);   o = L.off_bnd + (NW + 1) * kRing * 4;           // ring 0: constant sentinel (the row above token 0), ring w+1: last row of warp w
     L.off_zero = alb_align(o, 128); o = L.off_zero + kZeroChunk;
     L.off_ring = alb_align(o, 128); o = L.off_ring + NW * NS * L.stage_bytes;
     L.off_bits = alb_align(o, 16);  o = L.off_bits + (bits_smem ? (uint32_t)nblk * NW * RW * 4 : 0);
-    L.off_dur = alb_align(o, 16);   o = L.off_dur + (want_dur ? NW * RW * 4 : 0);
+    L.off_dur = alb_align(o, 16);   o = L.off_dur + (want_dur ? nc * NW * RW * 4 : 0);
     L.off_bt = alb_align(o, 16);    o = L.off_bt + (uint32_t)nblk * 8 + 16;                 // backtrack hand-off: (token, step mask) per 32-frame block + cursor
     L.total = alb_align(o, 16);
     return L;
@@ -182,6 +183,27 @@ __device__ __forceinline__ float lds32(uint32_t a) {
 __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w));
 }
+// ---- thread-block cluster helpers (an utterance too long for one CTA's fast form is split over the CTAs of a cluster)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {       // same shared-memory offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// flag after data, same thread: release at cluster scope orders the remote data stores before the remote flag store
+__device__ __forceinline__ void st_cluster_flag_release(uint32_t a, int v) {
+    asm volatile("st.release.cluster.shared::cluster.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_flag(uint32_t a, int v) {
+    asm volatile("st.relaxed.cluster.shared::cluster.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // Progress flags between neighbouring warps of one CTA.  Producer: the SAME lane stores the boundary
 // values and then the flag; consumer: reads the flag, then the values.  Shared-memory accesses of one
 // thread are performed in program order by the SM's in-order LSU pipe, so plain volatile accesses are
@@ -270,7 +292,7 @@ struct Fwd {
 //     after the unit, so the four groups stay one basic block.
 template <int R, int TF, int UNIT, bool SKEW, bool DIAG>
 __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint32_t tile_prev, uint32_t bin_addr, uint32_t bout_addr, int Y, int yl,
-                                             bool has_in, bool lane0, bool lane31, float neg, int dxy, uint32_t* bits_row, int TXS,
+                                             bool remote_out, bool lane0, bool lane31, float neg, int dxy, uint32_t* bits_row, int TXS,
                                              int y_lo, unsigned span)
 {
     constexpr int NG = UNIT / 4;
@@ -356,7 +378,11 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
                 for (int r = 0; r < R; ++r) vq[kk & 1][r] = lds32(a + (kk + 2) * 4 + r * (TF * 4));
             }
         }
-        if (lane31) sts128(bout_addr + (((Y + 4 * g) & (kRing - 1)) << 2), o4[0], o4[1], o4[2], o4[3]);
+        if (lane31) {
+            const uint32_t a = bout_addr + (((Y + 4 * g) & (kRing - 1)) << 2);
+            if (remote_out) st_cluster_v4(a, o4[0], o4[1], o4[2], o4[3]);      // the consumer is warp 0 of the next CTA of the cluster
+            else sts128(a, o4[0], o4[1], o4[2], o4[3]);
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             S.wbits[r] = __funnelshift_r(S.wbits[r], hb[r], 4);
@@ -531,7 +557,15 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     const int NS = p.ns;
     const bool is_loader = wid >= NW;
     const int w = is_loader ? wid - NW : wid;            // the compute warp this warp is, or serves
-    const int TXS = NW * RW;
+    // Cluster mode (p.nc > 1, latency regime, long utterances): the CTAs of a cluster split one utterance's token rows; CTA c
+    // owns compute warps c*NW .. c*NW+NW-1 of one long pipeline.  The only cross-CTA traffic is the boundary ring between the
+    // last warp of CTA c and warp 0 of CTA c+1 (remote shared-memory stores, polls stay local), bits go to the L2 slot, CTA 0
+    // backtracks.
+    const int NC = p.nc;
+    const int crank = NC > 1 ? (int)cluster_ctarank() : 0;
+    const int unit_id = NC > 1 ? (int)blockIdx.x / NC : (int)blockIdx.x;      // cluster index, or CTA index
+    const int gw = crank * NW + w;                       // position of this warp in the utterance's pipeline
+    const int TXS = NC * NW * RW;
     const int nthr = blockDim.x;
     const bool bits_smem = (p.bits_ws == nullptr);
     struct { uint32_t off_full, off_empty, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, off_bt, stage_bytes; } L =
@@ -542,13 +576,15 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     const uint32_t empty0 = smem0 + L.off_empty + w * NS * 8;
     const uint32_t tail_a = smem0 + L.off_flags;                    // frames finished by lane 31 of warp w at +4*w
     const uint32_t head_a = tail_a + 4 * NW;                        // frames finished by lane 0  of warp w at +4*w
+    const uint32_t xin_tail_a = head_a + 4 * NW;                    // cluster: progress of the previous CTA's last warp (written remotely)
+    const uint32_t xout_head_a = xin_tail_a + 4;                    // cluster: progress of the next CTA's warp 0 (written remotely)
     int* misc = reinterpret_cast<int*>(smem + L.off_misc);          // [0]=item [1]=t_x [2]=t_y
     double* msum = reinterpret_cast<double*>(smem + L.off_misc + 64);   // [warp][2] partial mask sums
     const uint32_t bnd_a = smem0 + L.off_bnd;
     const uint32_t zero_a = smem0 + L.off_zero;
     const uint32_t ring_a = smem0 + L.off_ring + w * NS * L.stage_bytes;
     uint32_t* bits = bits_smem ? reinterpret_cast<uint32_t*>(smem + L.off_bits)
-                               : p.bits_ws + (int64_t)blockIdx.x * p.bits_slot_words;
+                               : p.bits_ws + (int64_t)unit_id * p.bits_slot_words;
     int* durS = reinterpret_cast<int*>(smem + L.off_dur);
     volatile int* btTok = reinterpret_cast<volatile int*>(smem + L.off_bt);          // [nblk] token at the last frame of each block
     volatile uint32_t* btMov = reinterpret_cast<volatile uint32_t*>(smem + L.off_bt) + p.nblk;   // [nblk] frames at which the path steps down (bit 31-k)
@@ -559,7 +595,8 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, SKEW ? 1 : 32); mbar_init(empty0 + 8 * s, 32); }   // one arrival per lane (full, skewed: the TMA issuer)
     for (int i = tid; i < kZeroChunk / 16; i += nthr)
         reinterpret_cast<int4*>(smem + L.off_zero)[i] = make_int4(0, 0, 0, 0);
-    for (int i = tid; i < kRing; i += nthr) reinterpret_cast<float*>(smem + L.off_bnd)[i] = p.neg;
+    if (crank == 0)
+        for (int i = tid; i < kRing; i += nthr) reinterpret_cast<float*>(smem + L.off_bnd)[i] = p.neg;
     fence_mbar_init();
     fence_proxy_async_smem();
     __syncthreads();
@@ -569,7 +606,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     const int Ty = p.Ty;
     const float neg = p.neg;
 
-    int item = blockIdx.x;
+    int item = unit_id;
     const bool dbg_on = (p.dbg != nullptr);
     long long* dbg = dbg_on ? p.dbg + (int64_t)blockIdx.x * (2 * kMaxWarps + 2) * 2 : nullptr;
     bool first_item = true;
@@ -591,11 +628,16 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         }
         if (tid < NW) {
             st_flag(tail_a + 4 * tid, -(1 << 28));
-            st_flag(head_a + 4 * tid, tid * RW);
+            st_flag(head_a + 4 * tid, (crank * NW + tid) * RW);
+        }
+        if (tid == 0) {
+            st_flag(xin_tail_a, -(1 << 28));
+            st_flag(xout_head_a, (crank + 1) * NW * RW);
         }
         if (p.durations != nullptr)
             for (int i = tid; i < TXS; i += nthr) durS[i] = 0;
-        __syncthreads();
+        if (NC > 1) cluster_sync_all();      // every CTA's flags and rings are initialised before any remote store can land
+        else __syncthreads();
         int t_x, t_y;
         if (p.mask != nullptr) {          // sum the per-warp partials; truncation like astype(np.int32) (__init__.py:18-19)
             double ax = 0.0, ay = 0.0;
@@ -619,7 +661,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         if (tid == 0) st_flag(bt_cur_a, ((t_y - 1) >> 5) + 1);     // nothing published yet (ordered by the barrier after the forward pass)
 
         // ---- geometry of this warp's slice of the band
-        const int x0 = w * RW;
+        const int x0 = gw * RW;
         const bool active = valid && x0 < t_x;
         const int x1 = (x0 + RW < t_x) ? x0 + RW : t_x;
         const int nrows = x1 - x0;
@@ -635,7 +677,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             unsigned char* pbase = reinterpret_cast<unsigned char*>(p.paths) + item * item_elems * p.esize;
             unsigned char* zA = nullptr;
             int64_t zbytes = 0;
-            const int ltid = tid - NW * 32, lthr = NW * 32;
+            const int ltid = crank * NW * 32 + (tid - NW * 32), lthr = NC * NW * 32;   // loader thread index over the whole cluster
             if (zf) {
                 unsigned char* pend = pbase + item_elems * p.esize;
                 zA = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pbase) + 15) & ~uintptr_t(15));
@@ -649,9 +691,9 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                     zbytes = zE - zA;
                 }
             }
-            const int nact = valid ? (t_x + RW - 1) / RW : NW;     // loader warps that take part in the zero fill
+            const int nact = valid ? (t_x + RW - 1) / RW : NC * NW;   // loader warps that take part in the zero fill
             const int64_t nchunks = (zbytes + kZeroChunk - 1) / kZeroChunk;
-            int64_t zc = w;                                        // next chunk this warp issues
+            int64_t zc = gw;                                       // next chunk this warp issues
             auto issue_zero = [&](int n) {
                 if (lane == 0) {
                     for (int q = 0; q < n && zc < nchunks; ++q, zc += nact) {
@@ -668,7 +710,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 constexpr int RPI = 32 / CPR;                       // row segments per warp instruction
                 const int ck = lane % CPR, q0 = lane / CPR;
                 const int my_tiles = t_e - t_s;
-                const int64_t my_chunks = (nchunks > w) ? (nchunks - w + nact - 1) / nact : 0;
+                const int64_t my_chunks = (nchunks > gw) ? (nchunks - gw + nact - 1) / nact : 0;
                 const int zq = (int)((my_chunks + my_tiles - 1) / (my_tiles > 0 ? my_tiles : 1));
                 long long l_e = 0, l_c = 0, l_z = 0, l0 = 0, l1 = 0, l2 = 0;
                 for (int t = t_s; t < t_e; ++t) {
@@ -720,21 +762,26 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                     e[0] = l_e; e[1] = l_c; e[2] = l_z; e[3] = t_e - t_s;
                 }
             }
-            if (zf && w < nact) {
+            if (zf && gw < nact) {
                 issue_zero(0x7fffffff);
                 if (lane == 0) { bulk_commit(); bulk_wait_all(); fence_proxy_async_global(); }
             }
         } else if (active) {
             // ================= compute warp: forward pass for rows [x0, x1) =================
-            const bool has_in = (w > 0);
+            const bool has_in = (gw > 0);
             const bool has_consumer = (x1 < t_x);
+            const bool remote_in = (w == 0 && crank > 0);                        // our producer is the last warp of the previous CTA
+            const bool remote_out = (NC > 1 && w == NW - 1 && has_consumer);               // our consumer is warp 0 of the next CTA (has_consumer => there is one)
             const bool lane0 = (lane == 0), lane31 = (lane == 31);
             const int xl0 = x0 + lane * R;
             const int lag = SKEW ? kSkewLag * lane : 0;
             const uint32_t bin_addr = bnd_a + w * kRing * 4;           // warp 0 reads the constant sentinel ring: x == 0, y > 0: v_prev = max_neg_val (core.pyx:27)
-            const uint32_t bout_addr = bnd_a + (w + 1) * kRing * 4;
+            const uint32_t bout_addr = remote_out ? mapa_u32(bnd_a, (uint32_t)crank + 1) : bnd_a + (w + 1) * kRing * 4;   // next CTA's ring 0
             const uint32_t my_tail = tail_a + 4 * w, my_head = head_a + 4 * w;
-            const uint32_t in_tail = tail_a + 4 * (has_in ? w - 1 : 0), out_head = head_a + 4 * (has_consumer ? w + 1 : w);
+            const uint32_t in_tail = remote_in ? xin_tail_a : tail_a + 4 * (w > 0 ? w - 1 : 0);
+            const uint32_t out_head = remote_out ? xout_head_a : head_a + 4 * (has_consumer ? w + 1 : w);
+            const uint32_t r_tail = remote_out ? mapa_u32(xin_tail_a, (uint32_t)crank + 1) : 0u;    // where the next CTA polls our progress
+            const uint32_t r_head = remote_in ? mapa_u32(xout_head_a, (uint32_t)crank - 1) : 0u;    // where the previous CTA polls ours
             const int diag_end = SKEW ? x0 + RW + LAG31 : x1;      // lane-0 frame from which no lane holds a row any more
 
             Fwd<R> S;
@@ -781,16 +828,16 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 const uint32_t tile_prev = (SKEW && y > y_start) ? ring_a + prev_stage * L.stage_bytes + lane * LANE_STRIDE : tile_addr;
                 const int yl = y - lag;
                 if (y < diag_end)
-                    forward_unit<R, TF, UNIT, SKEW, true>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, has_in, lane0, lane31, neg,
+                    forward_unit<R, TF, UNIT, SKEW, true>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, remote_out, lane0, lane31, neg,
                                                           xl0 - yl, bits_row, TXS, y_start, (unsigned)span);
                 else
-                    forward_unit<R, TF, UNIT, SKEW, false>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, has_in, lane0, lane31, neg,
+                    forward_unit<R, TF, UNIT, SKEW, false>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, remote_out, lane0, lane31, neg,
                                                            0, bits_row, TXS, y_start, (unsigned)span);
                 seen_in = next_in;
                 seen_cons = next_cons;
                 if (dbg_on) { c3 = clock64(); c_full += c1 - c0; c_poll += c2 - c1; c_unit += c3 - c2; }
-                if (lane31) st_flag(my_tail, y + UNIT);
-                if (lane0) st_flag(my_head, y + UNIT);
+                if (lane31) { st_flag(my_tail, y + UNIT); if (remote_out) st_cluster_flag_release(r_tail, y + UNIT); }
+                if (lane0) { st_flag(my_head, y + UNIT); if (remote_in) st_cluster_flag(r_head, y + UNIT); }
                 if (((y + UNIT) & (TF - 1)) == 0) {                 // tile consumed: hand the stage back to the loader
                     if (SKEW) {                                     // the trailing lanes still read this tile during the next unit
                         if (y > y_start) mbar_arrive(empty0 + 8 * prev_stage);
@@ -802,20 +849,21 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 }
             }
             if (SKEW && y_end > y_start) mbar_arrive(empty0 + 8 * prev_stage);
-            if (lane31) st_flag(my_tail, kProgDone);
+            if (lane31) { st_flag(my_tail, kProgDone); if (remote_out) st_cluster_flag_release(r_tail, kProgDone); }
             if (dbg_on && first_item && lane == 0) {
                 long long* e = p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + w) * 4;
                 e[0] = c_full; e[1] = c_poll; e[2] = c_unit; e[3] = (y_end - y_start) / UNIT;
             }
         }
         if (dbg_on && first_item && lane == 0) dbg[wid * 2 + 1] = clock64();
-        __syncthreads();
+        if (NC > 1) cluster_sync_all();      // all CTAs' direction bits (L2 slot) and zero fill are complete and visible
+        else __syncthreads();
 
         // ================= backtrack =================
         // Warp 0 walks: 32 frames per step, one find-leading-one chain per step DOWN (about t_x/t_y of the frames).  It only
         // publishes (token at the block's last frame, mask of step frames) per block; the other warps turn those into
         // stores, so address arithmetic and memory traffic are off the serial chain.
-        const int top = (t_y - 1) >> 5;
+        const int top = (crank == 0) ? (t_y - 1) >> 5 : -1;      // cluster: CTA 0 backtracks, the others are done
         if (wid == 0) {
             if (bits_smem) backtrack_walk<2>(bits, TXS, t_x, t_y, top, lane, smem0 + L.off_ring, btTok, btMov, bt_cur_a,
                                              dbg_on && first_item ? p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4 : nullptr);
@@ -823,7 +871,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                                              dbg_on && first_item ? p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4 : nullptr);
             fence_proxy_async_smem();   // the row windows went through the generic proxy into ring memory that TMA writes next
         } else {
-            if (p.frame_tok != nullptr)
+            if (p.frame_tok != nullptr && crank == 0)
                 for (int yy = t_y + (tid - 32); yy < Ty; yy += nthr - 32) p.frame_tok[(int64_t)item * Ty + yy] = -1;
             const int nemit = (nthr >> 5) - 1;                    // every warp but the walker
             for (int blk = top - (wid - 1); blk >= 0; blk -= nemit) {
@@ -842,19 +890,19 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             }
         }
         __syncthreads();
-        if (p.durations != nullptr)
+        if (p.durations != nullptr && crank == 0)
             for (int i = tid; i < p.Tx; i += nthr) p.durations[(int64_t)item * p.Tx + i] = (i < t_x) ? durS[i] : 0;
 
         if (dbg_on && first_item && tid == 0) dbg[2 * kMaxWarps * 2 + 1] = clock64();
         first_item = false;
         // ---- next item
-        if (p.B <= (int)gridDim.x) break;
+        if (NC > 1 || p.B <= (int)gridDim.x) break;
         if (tid == 0) misc[0] = atomicAdd(&p.ws->counter, 1) + (int)gridDim.x;
         __syncthreads();
         item = misc[0];
     }
 
-    if (p.B > (int)gridDim.x && tid == 0) {
+    if (NC == 1 && p.B > (int)gridDim.x && tid == 0) {
         const int d = atomicAdd(&p.ws->done, 1);
         if (d == (int)gridDim.x - 1) {      // last CTA out re-arms the counters for the next launch
             p.ws->counter = 0;

@@ -8,6 +8,7 @@ import torch
 
 from conftest import make_values, prefix_mask_np, random_lengths
 from oracle import mas as oracle
+from aligner_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 
@@ -81,6 +82,35 @@ def test_differential_small(ma, monkeypatch, force, kind):
         values = make_values(rng, kind, (b, tx, ty))
         t_x, t_y = random_lengths(rng, b, tx, ty, full=(trial == 0))
         check_against_oracle(ma, values, t_x, t_y)
+
+
+# ------------------------------------------------------------------ cluster mode: one utterance split over the CTAs of a cluster
+@pytest.mark.parametrize("force,txmax", [("1,32,3,0,1,2", 256), ("2,32,3,0,1,2", 512), ("2,32,2,0,1,4", 1024), ("1,32,4,0,1,8", 1024),
+                                         ("3,32,2,0,1,3", 1152)])
+def test_cluster_mode_forced(ma, monkeypatch, force, txmax):
+    monkeypatch.setenv("ALB200_FORCE", force)
+    rng = np.random.default_rng(abs(hash(force)) % (2 ** 31))
+    for trial in range(3):
+        b = int(rng.integers(1, 6))
+        tx = int(rng.integers(txmax // 2, txmax + 1))
+        ty = (int(rng.integers(tx, tx + 600)) + 3) // 4 * 4          # cluster mode needs 16-byte aligned rows
+        values = make_values(rng, ["gauss", "ties", "sentinel"][trial], (b, tx, ty))
+        t_x, t_y = random_lengths(rng, b, tx, ty, full=(trial == 0))
+        assert "cluster=%s" % force.split(",")[5] in _lib.describe(b, tx, ty)
+        check_against_oracle(ma, values, t_x, t_y)
+
+
+def test_cluster_mode_is_the_default_for_long_text(ma):
+    rng = np.random.default_rng(5)
+    b, tx, ty = 3, 1000, 1400
+    assert "cluster=4" in _lib.describe(b, tx, ty)
+    values = make_values(rng, "gauss", (b, tx, ty))
+    t_x, t_y = random_lengths(rng, b, tx, ty, full=True)
+    check_against_oracle(ma, values, t_x, t_y)
+    t_x, t_y = random_lengths(rng, b, tx, ty)                          # short items leave whole CTAs of a cluster idle
+    t_x[0], t_y[0] = 7, 9
+    check_against_oracle(ma, values, t_x, t_y)
+    assert "cluster=1" in _lib.describe(148, tx, ty)                   # not when the clusters would not all be resident
 
 
 @pytest.mark.parametrize("skew", ["0", "1"])

@@ -73,7 +73,9 @@ def main():
         "c2": (64, 200, 1000, False, [None, "2,32,4,1,0", "2,32,3,1,1", "2,32,4,1,1", "2,32,5,1,1", "2,32,5,0,1", "2,32,6,0,1", "2,32,8,0,1",
                                       "3,32,4,1,1", "4,32,4,1,1"]),
         "c3": (32, 300, 1500, False, [None, "3,32,3,0,0", "3,32,3,0,1", "3,32,4,0,1", "4,32,3,0,1", "2,32,3,0,1", "2,32,4,0,1", "1,32,3,0,1"]),
-        "c4": (8, 1000, 6000, False, [None, "8,16,2,0,0", "8,32,2,0,1", "4,32,2,0,1", "4,32,3,0,1", "6,32,2,0,1"]),
+        "c4": (8, 1000, 6000, False, [None, "8,16,2,0,0,1", "2,32,3,0,1,4", "2,32,2,0,1,4", "3,32,2,0,1,3", "4,32,2,0,1,2", "4,32,3,0,1,2", "1,32,4,0,1,8"]),
+        "c4b": (16, 768, 3072, False, [None, "6,16,4,0,0,1", "2,32,3,0,1,3", "3,32,2,0,1,2", "4,32,2,0,1,2"]),
+        "c4c": (32, 640, 3200, False, [None, "6,16,4,0,0,1", "2,32,3,0,1,3", "4,32,2,0,1,2"]),
         "c5a": (2048, 400, 2000, True, [None, "4,16,3,0,0", "8,16,2,0,0", "8,16,3,0,0", "8,8,3,0,0", "8,8,4,0,0", "6,16,2,0,0", "8,32,2,0,0"]),
         "c5b": (4096, 200, 1000, False, [None, "4,16,2,0,0", "4,16,3,0,0", "4,32,2,0,0", "4,32,2,1,0", "6,16,2,0,0", "8,16,2,0,0", "3,16,2,0,0"]),
         "c5c": (4096, 100, 800, False, [None, "2,16,2,0,0", "2,16,3,0,0", "2,32,2,0,0", "4,16,2,0,0", "4,32,2,1,0", "1,32,2,1,0"]),
