@@ -61,6 +61,7 @@ struct KEntry { int R, TF, skew, nwmax, minb; KernelFn fn; };
 #define ALB_K(R, TF) { R, TF, 0, 4, 1, mas_kernel<R, TF, false, 4, 1> }, { R, TF, 0, 4, 2, mas_kernel<R, TF, false, 4, 2> }
 #define ALB_KS(R) { R, 32, 1, 4, 1, mas_kernel<R, 32, true, 4, 1> }
 #define ALB_K8(R, TF) { R, TF, 0, 8, 1, mas_kernel<R, TF, false, 8, 1> }
+#define ALB_KC(R) { R, 32, 2, 4, 1, mas_kernel<R, 32, true, 4, 1, true> }      // skew code 2 = skewed + cluster hand-off
 #define ALB_KS8(R) { R, 32, 1, 8, 1, mas_kernel<R, 32, true, 8, 1> }
 static const KEntry g_kernels[] = {
     ALB_K(1, 32),
@@ -74,6 +75,7 @@ static const KEntry g_kernels[] = {
     ALB_K8(16, 16), ALB_K8(16, 8),
     ALB_KS(1), ALB_KS(2), ALB_KS(3), ALB_KS(4), ALB_KS(6), ALB_KS(8),     // skewed: 32-frame tiles only
     ALB_KS8(1), ALB_KS8(2), ALB_KS8(3), ALB_KS8(4), ALB_KS8(8),
+    ALB_KC(1), ALB_KC(2), ALB_KC(3), ALB_KC(4),
 };
 static KernelFn find_kernel(int R, int TF, int skew, int nw, int minb)
 {
@@ -180,7 +182,7 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     if (!latency && !c->skew)
         for (const KEntry& k : g_kernels)
             if (k.R == R && k.TF == best_tf && k.skew == 0 && NW <= k.nwmax && k.minb == 2) { c->fn = k.fn; break; }
-    if (!c->fn) c->fn = find_kernel(R, best_tf, c->skew, NW, 1);
+    if (!c->fn) c->fn = find_kernel(R, best_tf, NC > 1 ? 2 : c->skew, NW, 1);
     if (!c->fn) return fail(ALB200_E_UNSUPPORTED, "no kernel instance for R=%s%lld TF=%lld", "", R, best_tf);
     SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur, want_skew, NC);
     c->smem = L.total;
@@ -297,7 +299,7 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
     p.nw = c.NW; p.ns = c.NS; p.nblk = (ty + 31) / 32; p.nc = c.nc;
     {
         const SmemLayout L = make_layout(c.NW, c.NS, c.R, c.TF, c.bits_smem, p.nblk, durations != nullptr, c.skew, c.nc);
-        p.off_full = L.off_full; p.off_empty = L.off_empty; p.off_flags = L.off_flags; p.off_misc = L.off_misc; p.off_bnd = L.off_bnd;
+        p.off_full = L.off_full; p.off_empty = L.off_empty; p.off_xbar = L.off_xbar; p.off_flags = L.off_flags; p.off_misc = L.off_misc; p.off_bnd = L.off_bnd;
         p.off_zero = L.off_zero; p.off_ring = L.off_ring; p.off_bits = L.off_bits; p.off_dur = L.off_dur; p.off_bt = L.off_bt; p.stage_bytes = L.stage_bytes;
     }
     p.aligned = aligned ? 1 : 0;

@@ -90,11 +90,11 @@ struct MasParams {
     int aligned;                // values base and Ty allow 16-byte copies
     int nc;                     // CTAs per utterance (thread-block cluster; 1 = one CTA per utterance)
     float neg;
-    uint32_t off_full, off_empty, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, off_bt, stage_bytes;   // make_layout(), done on the host
+    uint32_t off_full, off_empty, off_xbar, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, off_bt, stage_bytes;   // make_layout(), done on the host
 };
 
 struct SmemLayout {
-    uint32_t off_full, off_empty, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, off_bt, total;
+    uint32_t off_full, off_empty, off_xbar, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, off_bt, total;
     uint32_t stage_bytes;
 };
 
@@ -109,7 +109,8 @@ __host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF,
     uint32_t o = 0;
     L.off_full = o;  o += NW * NS * 8;
     L.off_empty = o; o += NW * NS * 8;
-    L.off_flags = alb_align(o, 16); o = L.off_flags + (2 * NW + 2) * 4;    // tail (lane 31) and head (lane 0) progress per warp, + the two cross-CTA slots
+    L.off_xbar = o;  o += (nc > 1 ? 4 * 8 : 0);
+    L.off_flags = alb_align(o, 16); o = L.off_flags + (2 * NW + 1) * 4;    // tail (lane 31) and head (lane 0) progress per warp, + the cross-CTA slot
     L.off_misc = alb_align(o, 16);  o = L.off_misc + 64 + 2 * kMaxWarps * 16; // item/lengths + per-warp partial mask sums
     L.off_bnd = alb_align(o, 16);   o = L.off_bnd + (NW + 1) * kRing * 4;           // ring 0: constant sentinel (the row above token 0), ring w+1: last row of warp w
     L.off_zero = alb_align(o, 128); o = L.off_zero + kZeroChunk;
@@ -190,12 +191,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {    
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t a, float x, float y, float z, float w) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
-// flag after data, same thread: release at cluster scope orders the remote data stores before the remote flag store
-__device__ __forceinline__ void st_cluster_flag_release(uint32_t a, int v) {
-    asm volatile("st.release.cluster.shared::cluster.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+// shared -> remote shared bulk copy (async proxy); the bytes complete on an mbarrier of the destination CTA.  This is the
+// fence-free way to hand data to another CTA: a release store at cluster scope compiles to MEMBAR.ALL.GPU (~2000 cycles).
+__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
 }
 __device__ __forceinline__ void st_cluster_flag(uint32_t a, int v) {
     asm volatile("st.relaxed.cluster.shared::cluster.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
@@ -292,7 +292,7 @@ struct Fwd {
 //     after the unit, so the four groups stay one basic block.
 template <int R, int TF, int UNIT, bool SKEW, bool DIAG>
 __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint32_t tile_prev, uint32_t bin_addr, uint32_t bout_addr, int Y, int yl,
-                                             bool remote_out, bool lane0, bool lane31, float neg, int dxy, uint32_t* bits_row, int TXS,
+                                             bool lane0, bool lane31, float neg, int dxy, uint32_t* bits_row, int TXS,
                                              int y_lo, unsigned span)
 {
     constexpr int NG = UNIT / 4;
@@ -378,11 +378,7 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
                 for (int r = 0; r < R; ++r) vq[kk & 1][r] = lds32(a + (kk + 2) * 4 + r * (TF * 4));
             }
         }
-        if (lane31) {
-            const uint32_t a = bout_addr + (((Y + 4 * g) & (kRing - 1)) << 2);
-            if (remote_out) st_cluster_v4(a, o4[0], o4[1], o4[2], o4[3]);      // the consumer is warp 0 of the next CTA of the cluster
-            else sts128(a, o4[0], o4[1], o4[2], o4[3]);
-        }
+        if (lane31) sts128(bout_addr + (((Y + 4 * g) & (kRing - 1)) << 2), o4[0], o4[1], o4[2], o4[3]);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             S.wbits[r] = __funnelshift_r(S.wbits[r], hb[r], 4);
@@ -541,7 +537,7 @@ __device__ __forceinline__ void backtrack_walk(const uint32_t* bits, int TXS, in
 // ------------------------------------------------------------------ the kernel
 // NWMAX bounds the compute warps of an instance (4 -> 256 threads, 8 -> 512 threads).  MINB = 2 holds an instance to 128
 // registers so two CTAs share an SM (throughput regime); MINB = 1 lets an utterance that owns its SM use up to 255.
-template <int R, int TF, bool SKEW, int NWMAX, int MINB>
+template <int R, int TF, bool SKEW, int NWMAX, int MINB, bool CL = false>
 __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasParams p, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int RW = 32 * R;
@@ -561,7 +557,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     // owns compute warps c*NW .. c*NW+NW-1 of one long pipeline.  The only cross-CTA traffic is the boundary ring between the
     // last warp of CTA c and warp 0 of CTA c+1 (remote shared-memory stores, polls stay local), bits go to the L2 slot, CTA 0
     // backtracks.
-    const int NC = p.nc;
+    const int NC = CL ? p.nc : 1;                        // CL instances only: the single-CTA instances carry none of this
     const int crank = NC > 1 ? (int)cluster_ctarank() : 0;
     const int unit_id = NC > 1 ? (int)blockIdx.x / NC : (int)blockIdx.x;      // cluster index, or CTA index
     const int gw = crank * NW + w;                       // position of this warp in the utterance's pipeline
@@ -576,8 +572,8 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     const uint32_t empty0 = smem0 + L.off_empty + w * NS * 8;
     const uint32_t tail_a = smem0 + L.off_flags;                    // frames finished by lane 31 of warp w at +4*w
     const uint32_t head_a = tail_a + 4 * NW;                        // frames finished by lane 0  of warp w at +4*w
-    const uint32_t xin_tail_a = head_a + 4 * NW;                    // cluster: progress of the previous CTA's last warp (written remotely)
-    const uint32_t xout_head_a = xin_tail_a + 4;                    // cluster: progress of the next CTA's warp 0 (written remotely)
+    const uint32_t xout_head_a = head_a + 4 * NW;                   // cluster: progress of the next CTA's warp 0 (written remotely)
+    const uint32_t xbar_a = smem0 + p.off_xbar;                     // cluster: 4 mbarriers, one per 32-slot quarter of the incoming boundary ring
     int* misc = reinterpret_cast<int*>(smem + L.off_misc);          // [0]=item [1]=t_x [2]=t_y
     double* msum = reinterpret_cast<double*>(smem + L.off_misc + 64);   // [warp][2] partial mask sums
     const uint32_t bnd_a = smem0 + L.off_bnd;
@@ -591,6 +587,8 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     const uint32_t bt_cur_a = smem0 + L.off_bt + 8 * (uint32_t)p.nblk;              // lowest block the walker has published
 
     // ---- one-time setup
+    if (CL && tid == 0)
+        for (int q = 0; q < 4; ++q) mbar_init(xbar_a + 8 * q, 1);
     if (!is_loader && lane == 0)
         for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, SKEW ? 1 : 32); mbar_init(empty0 + 8 * s, 32); }   // one arrival per lane (full, skewed: the TMA issuer)
     for (int i = tid; i < kZeroChunk / 16; i += nthr)
@@ -630,10 +628,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             st_flag(tail_a + 4 * tid, -(1 << 28));
             st_flag(head_a + 4 * tid, (crank * NW + tid) * RW);
         }
-        if (tid == 0) {
-            st_flag(xin_tail_a, -(1 << 28));
-            st_flag(xout_head_a, (crank + 1) * NW * RW);
-        }
+        if (tid == 0) st_flag(xout_head_a, (crank + 1) * NW * RW);
         if (p.durations != nullptr)
             for (int i = tid; i < TXS; i += nthr) durS[i] = 0;
         if (NC > 1) cluster_sync_all();      // every CTA's flags and rings are initialised before any remote store can land
@@ -776,12 +771,29 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             const int xl0 = x0 + lane * R;
             const int lag = SKEW ? kSkewLag * lane : 0;
             const uint32_t bin_addr = bnd_a + w * kRing * 4;           // warp 0 reads the constant sentinel ring: x == 0, y > 0: v_prev = max_neg_val (core.pyx:27)
-            const uint32_t bout_addr = remote_out ? mapa_u32(bnd_a, (uint32_t)crank + 1) : bnd_a + (w + 1) * kRing * 4;   // next CTA's ring 0
+            const uint32_t bout_addr = bnd_a + (w + 1) * kRing * 4;
             const uint32_t my_tail = tail_a + 4 * w, my_head = head_a + 4 * w;
-            const uint32_t in_tail = remote_in ? xin_tail_a : tail_a + 4 * (w > 0 ? w - 1 : 0);
+            const uint32_t in_tail = tail_a + 4 * (w > 0 ? w - 1 : 0);
             const uint32_t out_head = remote_out ? xout_head_a : head_a + 4 * (has_consumer ? w + 1 : w);
-            const uint32_t r_tail = remote_out ? mapa_u32(xin_tail_a, (uint32_t)crank + 1) : 0u;    // where the next CTA polls our progress
-            const uint32_t r_head = remote_in ? mapa_u32(xout_head_a, (uint32_t)crank - 1) : 0u;    // where the previous CTA polls ours
+            // Cluster hand-off: the producer (last warp of CTA c) writes its local ring as usual and, once per unit, lane 31
+            // ships the unit's 32 boundary values to ring 0 of CTA c+1 with ONE shared->remote-shared bulk copy whose bytes
+            // complete on an mbarrier over there; the consumer arms and waits on that mbarrier.  No fences on either side.
+            const uint32_t r_ring = remote_out ? mapa_u32(bnd_a, (uint32_t)crank + 1) : 0u;         // next CTA's ring 0
+            const uint32_t r_xbar = remote_out ? mapa_u32(xbar_a, (uint32_t)crank + 1) : 0u;
+            const uint32_t r_head = remote_in ? mapa_u32(xout_head_a, (uint32_t)crank - 1) : 0u;    // where the previous CTA polls our progress
+            // producer geometry as seen by a remote consumer (the producer is a full warp of rows [x0 - RW, x0))
+            const int p_start = x0 - RW;
+            const int p_units = (((t_y - t_x + x0 - p_start + 31) & ~31) + 32) >> 5;                  // its (y_end - y_start) / 32
+            int xk = 0;                                          // producer units received so far
+            auto wait_remote = [&](int progress_needed) {        // producer progress is counted in its lane-0 steps
+                int k_need = ((progress_needed - p_start) >> 5) - 1;
+                if (k_need > p_units - 1) k_need = p_units - 1;
+                while (xk <= k_need) {
+                    if (lane0) mbar_expect_tx(xbar_a + 8 * (xk & 3), 128);
+                    mbar_wait(xbar_a + 8 * (xk & 3), (uint32_t)(xk >> 2) & 1u);
+                    ++xk;
+                }
+            };
             const int diag_end = SKEW ? x0 + RW + LAG31 : x1;      // lane-0 frame from which no lane holds a row any more
 
             Fwd<R> S;
@@ -794,7 +806,8 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             if (!has_in) {
                 S.bprev = 0.f;                                      // x == 0, y == 0: v_prev = 0 (core.pyx:25)
             } else {
-                while (ld_flag(in_tail) < y_start + UNIT + (SKEW ? 32 : 0)) { }
+                if (CL && remote_in) wait_remote(y_start + UNIT + 32);
+                else while (ld_flag(in_tail) < y_start + UNIT + (SKEW ? 32 : 0)) { }
                 if (SKEW) {
                     const float4 b = lds128(bin_addr + (((y_start + 28) & (kRing - 1)) << 2));   // frames y_start-4 .. y_start-1 (+31)
                     S.bprev = b.z; S.bprev1 = b.w;
@@ -805,7 +818,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             int seen_cons = has_consumer ? 0 : kProgDone;
             uint32_t prev_stage = 0;
             constexpr int IN_LEAD = SKEW ? 32 : 0;             // skewed: the producer's lane 31 trails its lane 0 by 31 steps
-            int seen_in = has_in ? y_start + UNIT + IN_LEAD : kProgDone;   // producer progress (in its steps) as last read
+            int seen_in = (has_in && !remote_in) ? y_start + UNIT + IN_LEAD : kProgDone;   // producer progress (in its steps) as last read
             uint32_t* bits_row = bits + xl0;
             long long c_full = 0, c_poll = 0, c_unit = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;   // ALB200_DBG cycle breakdown
 
@@ -814,6 +827,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 if (dbg_on) c0 = clock64();
                 if (fin == 0) mbar_wait(full0 + 8 * stage, phase);
                 if (dbg_on) c1 = clock64();
+                if (CL && remote_in) wait_remote(y + UNIT + IN_LEAD);
                 while (seen_in < y + UNIT + IN_LEAD) seen_in = ld_flag(in_tail);
                 {
                     const int need = SKEW ? y + UNIT - 32 - kRing : y + UNIT - (kRing - 4);   // our lane 31 is about to overwrite these ring slots
@@ -821,23 +835,32 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 }
                 // read now, needed after this unit (latency hidden): both neighbours' progress.  (Probing the next tile's barrier
                 // here with mbarrier.test_wait was measured: the probe itself costs ~800 cycles per unit -- profiles/r01_notes.md.)
-                const int next_in = has_in ? ld_flag(in_tail) : kProgDone;
+                const int next_in = (has_in && !remote_in) ? ld_flag(in_tail) : kProgDone;
                 const int next_cons = has_consumer ? ld_flag(out_head) : kProgDone;
                 if (dbg_on) c2 = clock64();
                 const uint32_t tile_addr = ring_a + stage * L.stage_bytes + lane * LANE_STRIDE + fin * 4;
                 const uint32_t tile_prev = (SKEW && y > y_start) ? ring_a + prev_stage * L.stage_bytes + lane * LANE_STRIDE : tile_addr;
                 const int yl = y - lag;
                 if (y < diag_end)
-                    forward_unit<R, TF, UNIT, SKEW, true>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, remote_out, lane0, lane31, neg,
+                    forward_unit<R, TF, UNIT, SKEW, true>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
                                                           xl0 - yl, bits_row, TXS, y_start, (unsigned)span);
                 else
-                    forward_unit<R, TF, UNIT, SKEW, false>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, remote_out, lane0, lane31, neg,
+                    forward_unit<R, TF, UNIT, SKEW, false>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
                                                            0, bits_row, TXS, y_start, (unsigned)span);
                 seen_in = next_in;
                 seen_cons = next_cons;
                 if (dbg_on) { c3 = clock64(); c_full += c1 - c0; c_poll += c2 - c1; c_unit += c3 - c2; }
-                if (lane31) { st_flag(my_tail, y + UNIT); if (remote_out) st_cluster_flag_release(r_tail, y + UNIT); }
-                if (lane0) { st_flag(my_head, y + UNIT); if (remote_in) st_cluster_flag(r_head, y + UNIT); }
+                if (lane31) st_flag(my_tail, y + UNIT);
+                if (lane0) st_flag(my_head, y + UNIT);
+                if (CL) {
+                    if (remote_out && lane31) {                  // ship this unit's 32 boundary values (written by this very lane)
+                        const uint32_t off = (uint32_t)(y & (kRing - 1)) << 2;
+                        const int k = (y - y_start) >> 5;
+                        fence_proxy_async_smem();                // generic-proxy writes above -> visible to the bulk copy
+                        bulk_s2c(r_ring + off, bout_addr + off, 128, r_xbar + 8 * (k & 3));   // the local slots are rewritten 4 units from now
+                    }
+                    if (remote_in && lane0) st_cluster_flag(r_head, y + UNIT);
+                }
                 if (((y + UNIT) & (TF - 1)) == 0) {                 // tile consumed: hand the stage back to the loader
                     if (SKEW) {                                     // the trailing lanes still read this tile during the next unit
                         if (y > y_start) mbar_arrive(empty0 + 8 * prev_stage);
@@ -849,7 +872,8 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 }
             }
             if (SKEW && y_end > y_start) mbar_arrive(empty0 + 8 * prev_stage);
-            if (lane31) { st_flag(my_tail, kProgDone); if (remote_out) st_cluster_flag_release(r_tail, kProgDone); }
+            if (lane31) st_flag(my_tail, kProgDone);
+            if (CL && remote_in) wait_remote(0x3fffffff);          // every incoming copy has landed before this CTA may leave the cluster barrier
             if (dbg_on && first_item && lane == 0) {
                 long long* e = p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + w) * 4;
                 e[0] = c_full; e[1] = c_poll; e[2] = c_unit; e[3] = (y_end - y_start) / UNIT;
