@@ -336,7 +336,7 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
     if (dbg) {
         long long* h = (long long*)malloc(dbg_n * 8);
         ALB_CUDA(cudaMemcpy(h, d_dbg, dbg_n * 8, cudaMemcpyDeviceToHost));
-        for (int cta = 0; cta < c.grid && cta < 2; ++cta) {
+        for (int cta = 0; cta < c.grid && cta < (c.nc > 1 ? c.nc : 2); ++cta) {
             long long* d = h + (size_t)cta * (2 * kMaxWarps + 2) * 2;
             const long long t0 = d[2 * kMaxWarps * 2];
             fprintf(stderr, "[alb200 dbg] cta %d: lengths %lld |", cta, d[0] - t0);
