@@ -268,7 +268,7 @@ static size_t ws_bytes_for(const Config& c)
 static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t_ys, const void* mask, int mask_dtype,
                       int64_t msb, int64_t msx, int64_t msy, void* paths, int esize, uint64_t one, int zero_fill,
                       int32_t* frame_tok, int32_t* durations, int32_t* lens_out, int b, int tx, int ty, float neg,
-                      void* workspace, size_t workspace_bytes, cudaStream_t stream)
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream, const int32_t* order = nullptr)
 {
     if (!values || b < 0 || tx <= 0 || ty <= 0) return fail(ALB200_E_INVALID, "null values or non-positive shape%s", "");
     if (!mask && (!t_xs || !t_ys)) return fail(ALB200_E_INVALID, "need lengths or a mask%s", "");
@@ -289,7 +289,7 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
         return fail(ALB200_E_INVALID, "workspace too small: %s%lld < %lld bytes", "", (long long)workspace_bytes, (long long)ws_bytes_for(c));
     MasParams p;
     memset(&p, 0, sizeof(p));
-    p.values = values; p.paths = paths; p.t_xs = t_xs; p.t_ys = t_ys;
+    p.values = values; p.paths = paths; p.t_xs = t_xs; p.t_ys = t_ys; p.order = order;
     p.mask = mask; p.msb = msb; p.msx = msx; p.msy = msy; p.mask_dtype = mask_dtype;
     p.frame_tok = frame_tok; p.durations = durations; p.lens_out = lens_out;
     p.ws = reinterpret_cast<WsHeader*>(workspace);
@@ -419,6 +419,14 @@ int alb200_mas_device(const float* values, const int32_t* t_xs, const int32_t* t
 {
     return launch_mas(values, t_xs, t_ys, nullptr, 0, 0, 0, 0, paths, path_elem_size, path_one, zero_fill, frame_tok,
                       durations, nullptr, b, tx, ty, max_neg_val, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int alb200_mas_device_ordered(const float* values, const int32_t* t_xs, const int32_t* t_ys, const int32_t* order, void* paths,
+                              int path_elem_size, uint64_t path_one, int zero_fill, int32_t* frame_tok, int32_t* durations, int b, int tx,
+                              int ty, float max_neg_val, void* workspace, size_t workspace_bytes, void* stream)
+{
+    return launch_mas(values, t_xs, t_ys, nullptr, 0, 0, 0, 0, paths, path_elem_size, path_one, zero_fill, frame_tok,
+                      durations, nullptr, b, tx, ty, max_neg_val, workspace, workspace_bytes, (cudaStream_t)stream, order);
 }
 
 int alb200_mas_device_masked(const float* values, const void* mask, int mask_dtype, int64_t msb, int64_t msx, int64_t msy,

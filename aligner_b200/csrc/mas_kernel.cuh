@@ -70,6 +70,7 @@ struct MasParams {
     void* paths;
     const int32_t* t_xs;
     const int32_t* t_ys;
+    const int32_t* order;       // optional permutation of [0, B): the persistent grid takes utterance order[i] as its i-th work item
     const void* mask;
     int64_t msb, msx, msy;
     int32_t* frame_tok;
@@ -605,6 +606,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     const float neg = p.neg;
 
     int item = unit_id;
+    if (p.order != nullptr && item < p.B) item = p.order[item];
     const bool dbg_on = (p.dbg != nullptr);
     long long* dbg = dbg_on ? p.dbg + (int64_t)blockIdx.x * (2 * kMaxWarps + 2) * 2 : nullptr;
     bool first_item = true;
@@ -921,7 +923,11 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         first_item = false;
         // ---- next item
         if (NC > 1 || p.B <= (int)gridDim.x) break;
-        if (tid == 0) misc[0] = atomicAdd(&p.ws->counter, 1) + (int)gridDim.x;
+        if (tid == 0) {
+            int nxt = atomicAdd(&p.ws->counter, 1) + (int)gridDim.x;
+            if (p.order != nullptr && nxt < p.B) nxt = p.order[nxt];
+            misc[0] = nxt;
+        }
         __syncthreads();
         item = misc[0];
     }

@@ -97,9 +97,13 @@ def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, return_durations: b
 def maximum_path_lengths(value: torch.Tensor, x_lengths: torch.Tensor, y_lengths: torch.Tensor, *,
                          out_dtype: torch.dtype | None = None, dense: bool = True,
                          return_durations: bool = False, return_frame_tokens: bool = False,
-                         max_neg_val: float = -1e9):
+                         max_neg_val: float = -1e9, order=None):
     """Mask-free entry: lengths given directly as int32 [b] CUDA tensors.
-    Returns a dict with any of 'path', 'durations' (int32 [b,t_x]), 'frame_tokens' (int32 [b,t_y], -1 past t_y)."""
+    Returns a dict with any of 'path', 'durations' (int32 [b,t_x]), 'frame_tokens' (int32 [b,t_y], -1 past t_y).
+
+    order: None (batch order), an int32 [b] CUDA permutation, or "lpt" = longest utterance first (descending
+    t_x*t_y, computed on the device): the persistent grid then starts the expensive items first, which shortens
+    the tail of a mixed-length batch.  The result does not depend on it."""
     v = _prep_value(value)
     b, tx, ty = v.shape
     dtype = out_dtype or value.dtype
@@ -116,8 +120,16 @@ def maximum_path_lengths(value: torch.Tensor, x_lengths: torch.Tensor, y_lengths
         if b > 0 and tx > 0 and ty > 0:
             stream = torch.cuda.current_stream(v.device).cuda_stream
             ws = _workspace(v.device, stream, b, tx, ty)
-            _lib.check(_lib.lib.alb200_mas_device(
-                v.data_ptr(), xl.data_ptr(), yl.data_ptr(),
+            if isinstance(order, str):
+                if order != "lpt":
+                    raise ValueError("order must be None, 'lpt' or an int32 permutation tensor")
+                order = torch.argsort(xl.to(torch.int64) * yl.to(torch.int64), descending=True, stable=True).to(torch.int32)
+            elif order is not None:
+                order = order.to(device=v.device, dtype=torch.int32).contiguous()
+                if order.numel() != b:
+                    raise ValueError("order must hold a permutation of range(b)")
+            _lib.check(_lib.lib.alb200_mas_device_ordered(
+                v.data_ptr(), xl.data_ptr(), yl.data_ptr(), order.data_ptr() if order is not None else None,
                 path.data_ptr() if dense else None, esize, one, 1,
                 ftok.data_ptr() if ftok is not None else None, dur.data_ptr() if dur is not None else None,
                 b, tx, ty, max_neg_val, ws.data_ptr(), ws.numel(), stream))

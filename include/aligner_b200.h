@@ -76,6 +76,16 @@ int alb200_mas_device(const float *values, const int32_t *t_xs, const int32_t *t
                       int b, int tx, int ty, float max_neg_val,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* Same as alb200_mas_device with a processing order: `order` is an int32 [b] device array holding a permutation
+ * of 0..b-1; the persistent grid takes utterance order[i] as its i-th work item.  Results are identical for any
+ * order (utterances are independent, core.pyx:44-45); handing over the longest utterances first (descending
+ * t_x*t_y) shortens the tail of a mixed-length batch.  NULL = batch order. */
+int alb200_mas_device_ordered(const float *values, const int32_t *t_xs, const int32_t *t_ys, const int32_t *order,
+                              void *paths, int path_elem_size, uint64_t path_one, int zero_fill,
+                              int32_t *frame_tok, int32_t *durations,
+                              int b, int tx, int ty, float max_neg_val,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
 /* Same, with the lengths derived inside the kernel from a [b,tx,ty] mask the way
  * the reference's Python layer does (monotonic_align/__init__.py:18-19):
  *   t_x = sum_x mask[b, x, 0],  t_y = sum_y mask[b, 0, y], truncated to int32.

@@ -84,6 +84,20 @@ def test_differential_small(ma, monkeypatch, force, kind):
         check_against_oracle(ma, values, t_x, t_y)
 
 
+def test_processing_order_does_not_change_results(ma):
+    """alb200_mas_device_ordered: any permutation (and the built-in longest-first order) gives the batch-order result."""
+    rng = np.random.default_rng(11)
+    b, tx, ty = 700, 60, 160                     # more utterances than resident CTAs: the work cursor is exercised
+    values = make_values(rng, "gauss", (b, tx, ty))
+    t_x, t_y = random_lengths(rng, b, tx, ty)
+    want = oracle_paths(values, t_x, t_y)
+    v, xl, yl = torch.from_numpy(values).cuda(), torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda()
+    for order in ("lpt", torch.from_numpy(rng.permutation(b).astype(np.int32)).cuda()):
+        out = ma.maximum_path_lengths(v, xl, yl, out_dtype=torch.int32, return_durations=True, order=order)
+        assert np.array_equal(out["path"].cpu().numpy(), want)
+        assert np.array_equal(out["durations"].cpu().numpy(), want.sum(-1))
+
+
 # ------------------------------------------------------------------ cluster mode: one utterance split over the CTAs of a cluster
 @pytest.mark.parametrize("force,txmax", [("1,32,3,0,1,2", 256), ("2,32,3,0,1,2", 512), ("2,32,2,0,1,4", 1024), ("1,32,4,0,1,8", 1024),
                                          ("3,32,2,0,1,3", 1152)])
