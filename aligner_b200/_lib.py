@@ -20,7 +20,7 @@ F32, F16, BF16, F64, U8, I8, I16, I32, I64 = range(9)
 
 # every symbol include/aligner_b200.h declares (tests check the export list against the header)
 SYMBOLS = (
-    "alb200_last_error", "alb200_version", "alb200_mas_device", "alb200_mas_device_ordered", "alb200_mas_device_masked",
+    "alb200_last_error", "alb200_version", "alb200_mas_device", "alb200_mas_device_ordered", "alb200_mas_device_ex", "alb200_mas_device_masked",
     "alb200_mas_workspace_bytes", "alb200_mas_status", "alb200_mas_describe", "alb200_maximum_path_c",
     "alb200_last_transfer_bytes", "alb200_launch_count",
     "alb200_neg_cent_gaussian", "alb200_neg_cent_ota",
@@ -50,6 +50,8 @@ def _load() -> ctypes.CDLL:
     lib.alb200_mas_device.restype = i32
     lib.alb200_mas_device_ordered.argtypes = [vp, vp, vp, vp, vp, i32, u64, i32, vp, vp, i32, i32, i32, f32, vp, sz, vp]
     lib.alb200_mas_device_ordered.restype = i32
+    lib.alb200_mas_device_ex.argtypes = [vp, i32, vp, vp, vp, i32, i64, i64, i64, vp, vp, i32, u64, i32, vp, vp, vp, i32, i32, i32, f32, vp, sz, vp]
+    lib.alb200_mas_device_ex.restype = i32
     lib.alb200_mas_device_masked.argtypes = [vp, vp, i32, i64, i64, i64, vp, i32, u64, i32, vp, vp, vp,
                                              i32, i32, i32, f32, vp, sz, vp]
     lib.alb200_mas_device_masked.restype = i32

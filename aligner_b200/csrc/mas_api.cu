@@ -55,7 +55,7 @@ static int device_info(DevInfo* out)
 
 // ------------------------------------------------------------------ kernel table
 typedef void (*KernelFn)(const MasParams, const CUtensorMap);
-struct KEntry { int R, TF, skew, nwmax, minb; KernelFn fn; };
+struct KEntry { int R, TF, skew, nwmax, minb; KernelFn fn; int vt; };     // vt: score element type (0 fp32, 1 fp16, 2 bf16)
 // lock-step form: a 255-register instance for the latency regime and a 128-register one for two CTAs per SM;
 // skewed form: latency regime only.
 #define ALB_K(R, TF) { R, TF, 0, 4, 1, mas_kernel<R, TF, false, 4, 1> }, { R, TF, 0, 4, 2, mas_kernel<R, TF, false, 4, 2> }
@@ -76,11 +76,20 @@ static const KEntry g_kernels[] = {
     ALB_KS(1), ALB_KS(2), ALB_KS(3), ALB_KS(4), ALB_KS(6), ALB_KS(8),     // skewed: 32-frame tiles only
     ALB_KS8(1), ALB_KS8(2), ALB_KS8(3), ALB_KS8(4), ALB_KS8(8),
     ALB_KC(1), ALB_KC(2), ALB_KC(3), ALB_KC(4),
+    // fp16 / bf16 score input, promoted on load: the skewed/TMA form for the latency regime and the 128-register lock-step
+    // form with 16-frame tiles for the throughput regime (the shapes the host picks); anything else reports
+    // ALB200_E_UNSUPPORTED and the caller promotes to fp32 on the device first
+#define ALB_KH(VT) \
+    { 1, 32, 1, 4, 1, mas_kernel<1, 32, true, 4, 1, false, VT>, VT }, { 2, 32, 1, 4, 1, mas_kernel<2, 32, true, 4, 1, false, VT>, VT },   \
+    { 3, 32, 1, 4, 1, mas_kernel<3, 32, true, 4, 1, false, VT>, VT }, { 4, 32, 1, 4, 1, mas_kernel<4, 32, true, 4, 1, false, VT>, VT },   \
+    { 2, 16, 0, 4, 2, mas_kernel<2, 16, false, 4, 2, false, VT>, VT }, { 4, 16, 0, 4, 2, mas_kernel<4, 16, false, 4, 2, false, VT>, VT }, \
+    { 8, 16, 0, 4, 2, mas_kernel<8, 16, false, 4, 2, false, VT>, VT }, { 16, 16, 0, 4, 2, mas_kernel<16, 16, false, 4, 2, false, VT>, VT }
+    ALB_KH(1), ALB_KH(2),
 };
-static KernelFn find_kernel(int R, int TF, int skew, int nw, int minb)
+static KernelFn find_kernel(int R, int TF, int skew, int nw, int minb, int vt)
 {
     for (const KEntry& k : g_kernels)
-        if (k.R == R && k.TF == TF && k.skew == skew && nw <= k.nwmax && k.minb <= minb) return k.fn;   // minb 1 also serves minb 2 requests
+        if (k.R == R && k.TF == TF && k.skew == skew && nw <= k.nwmax && k.minb <= minb && k.vt == vt) return k.fn;   // minb 1 also serves minb 2 requests
     return nullptr;
 }
 
@@ -97,7 +106,7 @@ struct Config {
 //   throughput regime (b > #SM): 4 rows per lane, and the smallest ring (>= 2 stages) that lets the 128-register
 //                    instances reach their register-limited occupancy (8 / compute-warps CTAs per SM), so that about 8
 //                    compute warps per SM hide each other's latency and one item's backtrack overlaps others' streaming.
-static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, Config* c)
+static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, int vt, Config* c)
 {
     const bool latency = b <= di.sms;
     int R, NW;
@@ -125,7 +134,7 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     // CTA, boundary rows handed over through distributed shared memory).  Only when every cluster gets its own SMs.
     int NC = 1;
     if (f_nc > 0) NC = f_nc;
-    else if (latency && aligned && tx > 512 && fr == 0 && f_skew != 0) {
+    else if (latency && aligned && tx > 512 && fr == 0 && f_skew != 0 && vt == 0) {
         const int want = (tx + 255) / 256;
         if (want <= 8 && (int64_t)b * want <= di.sms) NC = want;
     }
@@ -147,11 +156,12 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     if (!aligned || R > 8) want_skew = 0;                      // its tiles come in by TMA: 16-byte aligned rows, <= 256 rows per box
     auto try_fit = [&](int tf, int ns, int bs, int budget) -> bool {
         if (want_skew && tf != 32) return false;
+        if (vt && !want_skew && tf != 16) return false;          // half-precision lock-step instances exist for 16-frame tiles
         if (f_tf && tf != f_tf) return false;
         if (f_ns && ns != f_ns) return false;
         if (f_bits >= 0 && bs != f_bits) return false;
         if (NC > 1 && bs != 0) return false;                   // the walker (CTA 0) reads every CTA's bits: L2 slot
-        const SmemLayout L = make_layout(NW, ns, R, tf, bs, nblk, want_dur, want_skew, NC);
+        const SmemLayout L = make_layout(NW, ns, R, tf, bs, nblk, want_dur, want_skew, NC, vt ? 2 : 4);
         if ((int64_t)L.total > budget) return false;
         best_tf = tf; best_ns = ns; best_bits = bs;
         return true;
@@ -181,10 +191,10 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     c->fn = nullptr;
     if (!latency && !c->skew)
         for (const KEntry& k : g_kernels)
-            if (k.R == R && k.TF == best_tf && k.skew == 0 && NW <= k.nwmax && k.minb == 2) { c->fn = k.fn; break; }
-    if (!c->fn) c->fn = find_kernel(R, best_tf, NC > 1 ? 2 : c->skew, NW, 1);
-    if (!c->fn) return fail(ALB200_E_UNSUPPORTED, "no kernel instance for R=%s%lld TF=%lld", "", R, best_tf);
-    SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur, want_skew, NC);
+            if (k.R == R && k.TF == best_tf && k.skew == 0 && NW <= k.nwmax && k.minb == 2 && k.vt == vt) { c->fn = k.fn; break; }
+    if (!c->fn) c->fn = find_kernel(R, best_tf, NC > 1 ? 2 : c->skew, NW, latency ? 1 : 2, vt);
+    if (!c->fn) return fail(ALB200_E_UNSUPPORTED, "no kernel instance for R=%s%lld TF=%lld (score type %lld)", "", R, best_tf, vt);
+    SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur, want_skew, NC, vt ? 2 : 4);
     c->smem = L.total;
     c->bits_slot_words = (int64_t)nblk * NC * NW * 32 * R;
     ALB_CUDA(cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));   // once per instance, never lowered
@@ -197,15 +207,15 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
 }
 
 // select_config_uncached costs a few driver calls; remember the answers (per thread, tiny table).
-struct CfgKey { int dev, latency, tx, ty, dur, aligned, bclass; char env[48]; };
-static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, Config* c)
+struct CfgKey { int dev, latency, tx, ty, dur, aligned, bclass, vt; char env[48]; };
+static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, Config* c, int vt = 0)
 {
     static thread_local CfgKey keys[8];
     static thread_local Config vals[8];
     static thread_local int used = 0, next = 0;
     CfgKey k;
     memset(&k, 0, sizeof(k));
-    k.dev = di.dev; k.latency = b <= di.sms; k.tx = tx; k.ty = ty; k.dur = want_dur; k.aligned = aligned;
+    k.dev = di.dev; k.latency = b <= di.sms; k.tx = tx; k.ty = ty; k.dur = want_dur; k.aligned = aligned; k.vt = vt;
     k.bclass = (k.latency && tx > 512) ? b : 0;                 // the cluster decision depends on how many clusters fit
     if (const char* f = getenv("ALB200_FORCE")) strncpy(k.env, f, sizeof(k.env) - 1);
     int hit = -1;
@@ -213,7 +223,7 @@ static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur
         if (memcmp(&keys[i], &k, sizeof(k)) == 0) { hit = i; break; }
     if (hit < 0) {
         Config fresh;
-        int rc = select_config_uncached(di, b, tx, ty, want_dur, aligned, &fresh);
+        int rc = select_config_uncached(di, b, tx, ty, want_dur, aligned, vt, &fresh);
         if (rc) return rc;
         hit = next; next = (next + 1) % 8; if (used < 8) ++used;
         keys[hit] = k; vals[hit] = fresh;
@@ -228,7 +238,7 @@ static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur
 // loader fetches one box per tile (cp.async.bulk.tensor).  Encoding is host-side arithmetic; the last few are remembered.
 typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int values_tensor_map(const float* values, int b, int tx, int ty, int box_rows, int box_frames, CUtensorMap* out)
+static int values_tensor_map(const void* values, int vt, int b, int tx, int ty, int box_rows, int box_frames, CUtensorMap* out)
 {
     static TmapEncodeFn enc = nullptr;
     if (!enc) {
@@ -238,21 +248,22 @@ static int values_tensor_map(const float* values, int b, int tx, int ty, int box
         if (!fn || q != cudaDriverEntryPointSuccess) return fail(ALB200_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver%s", "");
         enc = reinterpret_cast<TmapEncodeFn>(fn);
     }
-    struct Key { const float* v; int b, tx, ty, br, bf; };
+    struct Key { const void* v; int b, tx, ty, br, bf, vt; };
     static thread_local Key keys[16];
     static thread_local CUtensorMap maps[16];
     static thread_local int used = 0, next = 0;
-    const Key k = { values, b, tx, ty, box_rows, box_frames };
+    const Key k = { values, b, tx, ty, box_rows, box_frames, vt };
     for (int i = 0; i < used; ++i)
-        if (keys[i].v == k.v && keys[i].b == b && keys[i].tx == tx && keys[i].ty == ty && keys[i].br == box_rows && keys[i].bf == box_frames) {
+        if (keys[i].v == k.v && keys[i].b == b && keys[i].tx == tx && keys[i].ty == ty && keys[i].br == box_rows && keys[i].bf == box_frames && keys[i].vt == vt) {
             *out = maps[i];
             return 0;
         }
     if ((int64_t)b * tx > 0x7fffffffLL) return fail(ALB200_E_UNSUPPORTED, "b * t_x = %s%lld rows exceed the tensor-map coordinate range", "", (long long)b * tx);
     cuuint64_t dims[2] = { (cuuint64_t)ty, (cuuint64_t)b * (cuuint64_t)tx };
-    cuuint64_t strides[1] = { (cuuint64_t)ty * 4 };
+    cuuint64_t strides[1] = { (cuuint64_t)ty * (vt ? 2 : 4) };
     cuuint32_t box[2] = { (cuuint32_t)box_frames, (cuuint32_t)box_rows }, es[2] = { 1, 1 };
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(values), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUtensorMapDataType dt = vt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (vt == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+    CUresult r = enc(out, dt, 2, const_cast<void*>(values), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ALB200_E_CUDA, "cuTensorMapEncodeTiled failed with %s%lld", "", (long long)r);
     keys[next] = k; maps[next] = *out;
@@ -265,10 +276,10 @@ static size_t ws_bytes_for(const Config& c)
     return sizeof(WsHeader) + (c.bits_smem ? 0 : (size_t)(c.grid / c.nc) * c.bits_slot_words * 4);
 }
 
-static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t_ys, const void* mask, int mask_dtype,
+static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_ys, const void* mask, int mask_dtype,
                       int64_t msb, int64_t msx, int64_t msy, void* paths, int esize, uint64_t one, int zero_fill,
                       int32_t* frame_tok, int32_t* durations, int32_t* lens_out, int b, int tx, int ty, float neg,
-                      void* workspace, size_t workspace_bytes, cudaStream_t stream, const int32_t* order = nullptr)
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream, const int32_t* order = nullptr, int vt = 0)
 {
     if (!values || b < 0 || tx <= 0 || ty <= 0) return fail(ALB200_E_INVALID, "null values or non-positive shape%s", "");
     if (!mask && (!t_xs || !t_ys)) return fail(ALB200_E_INVALID, "need lengths or a mask%s", "");
@@ -281,9 +292,10 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
     int rc = device_info(&di);
     if (rc) return rc;
     Config c;
-    bool aligned = (reinterpret_cast<uintptr_t>(values) & 15) == 0 && (ty & 3) == 0;
+    if (vt < 0 || vt > 2) return fail(ALB200_E_INVALID, "unknown score dtype %s%lld", "", vt);
+    bool aligned = (reinterpret_cast<uintptr_t>(values) & 15) == 0 && ((int64_t)ty * (vt ? 2 : 4)) % 16 == 0;
     if (getenv("ALB200_FORCE_UNALIGNED")) aligned = false;
-    rc = select_config(di, b, tx, ty, durations != nullptr, aligned, &c);
+    rc = select_config(di, b, tx, ty, durations != nullptr, aligned, &c, vt);
     if (rc) return rc;
     if (workspace_bytes < ws_bytes_for(c))
         return fail(ALB200_E_INVALID, "workspace too small: %s%lld < %lld bytes", "", (long long)workspace_bytes, (long long)ws_bytes_for(c));
@@ -298,7 +310,7 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
     p.B = b; p.Tx = tx; p.Ty = ty; p.esize = esize; p.zero_fill = zero_fill;
     p.nw = c.NW; p.ns = c.NS; p.nblk = (ty + 31) / 32; p.nc = c.nc;
     {
-        const SmemLayout L = make_layout(c.NW, c.NS, c.R, c.TF, c.bits_smem, p.nblk, durations != nullptr, c.skew, c.nc);
+        const SmemLayout L = make_layout(c.NW, c.NS, c.R, c.TF, c.bits_smem, p.nblk, durations != nullptr, c.skew, c.nc, vt ? 2 : 4);
         p.off_full = L.off_full; p.off_empty = L.off_empty; p.off_xbar = L.off_xbar; p.off_flags = L.off_flags; p.off_misc = L.off_misc; p.off_bnd = L.off_bnd;
         p.off_zero = L.off_zero; p.off_ring = L.off_ring; p.off_bits = L.off_bits; p.off_dur = L.off_dur; p.off_bt = L.off_bt; p.stage_bytes = L.stage_bytes;
     }
@@ -306,7 +318,7 @@ static int launch_mas(const float* values, const int32_t* t_xs, const int32_t* t
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (c.skew) {
-        rc = values_tensor_map(values, b, tx, ty, 32 * c.R, c.TF, &tmap);
+        rc = values_tensor_map(values, vt, b, tx, ty, 32 * c.R, c.TF, &tmap);
         if (rc) return rc;
     }
     p.neg = neg;
@@ -429,6 +441,22 @@ int alb200_mas_device_ordered(const float* values, const int32_t* t_xs, const in
                       durations, nullptr, b, tx, ty, max_neg_val, workspace, workspace_bytes, (cudaStream_t)stream, order);
 }
 
+int alb200_mas_device_ex(const void* values, int value_dtype, const int32_t* t_xs, const int32_t* t_ys, const void* mask, int mask_dtype,
+                         int64_t msb, int64_t msx, int64_t msy, const int32_t* order, void* paths, int path_elem_size, uint64_t path_one,
+                         int zero_fill, int32_t* frame_tok, int32_t* durations, int32_t* lens_out, int b, int tx, int ty, float max_neg_val,
+                         void* workspace, size_t workspace_bytes, void* stream)
+{
+    int vt;
+    switch (value_dtype) {
+        case ALB200_F32: vt = 0; break;
+        case ALB200_F16: vt = 1; break;
+        case ALB200_BF16: vt = 2; break;
+        default: return fail(ALB200_E_INVALID, "score dtype %s%lld is not fp32, fp16 or bf16", "", value_dtype);
+    }
+    return launch_mas(values, t_xs, t_ys, mask, mask_dtype, msb, msx, msy, paths, path_elem_size, path_one, zero_fill, frame_tok,
+                      durations, lens_out, b, tx, ty, max_neg_val, workspace, workspace_bytes, (cudaStream_t)stream, order, vt);
+}
+
 int alb200_mas_device_masked(const float* values, const void* mask, int mask_dtype, int64_t msb, int64_t msx, int64_t msy,
                              void* paths, int path_elem_size, uint64_t path_one, int zero_fill, int32_t* frame_tok,
                              int32_t* durations, int32_t* lens_out, int b, int tx, int ty, float max_neg_val,
@@ -446,7 +474,8 @@ size_t alb200_mas_workspace_bytes(int b, int tx, int ty)
     size_t need = sizeof(WsHeader);
     for (int v = 0; v < 4; ++v) {
         Config c;
-        if (select_config(di, b, tx, ty, (v & 1) != 0, (v & 2) != 0, &c) == 0) need = std::max(need, ws_bytes_for(c));
+        for (int vt = 0; vt < 3; ++vt)
+            if (select_config(di, b, tx, ty, (v & 1) != 0, (v & 2) != 0, &c, vt) == 0) need = std::max(need, ws_bytes_for(c));
     }
     return need;
 }

@@ -66,7 +66,7 @@ struct WsHeader {       // first 64 bytes of the workspace
 };
 
 struct MasParams {
-    const float* values;
+    const void* values;         // fp32, or fp16 / bf16 (promoted exactly on load; kernel instances are compiled per element type)
     void* paths;
     const int32_t* t_xs;
     const int32_t* t_ys;
@@ -102,11 +102,12 @@ struct SmemLayout {
 __host__ __device__ inline uint32_t alb_align(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 // dense: the stages are written by 2-D TMA box loads (skewed form): rows back to back, no per-lane skew
-__host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF, int bits_smem, int nblk, int want_dur, int dense = 0, int nc = 1)
+__host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF, int bits_smem, int nblk, int want_dur, int dense = 0, int nc = 1,
+                                                  int elem_bytes = 4)
 {
     SmemLayout L;
     const uint32_t RW = 32u * R;
-    L.stage_bytes = RW * TF * 4 + (dense ? 0 : 32 * kLanePad);
+    L.stage_bytes = RW * TF * elem_bytes + (dense ? 0 : 32 * kLanePad);
     uint32_t o = 0;
     L.off_full = o;  o += NW * NS * 8;
     L.off_empty = o; o += NW * NS * 8;
@@ -181,6 +182,23 @@ __device__ __forceinline__ float lds32(uint32_t a) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
     return v;
+}
+// Score element types: VT = 0 fp32, 1 fp16, 2 bf16.  Half types are promoted to fp32 on load -- exactly what the reference's
+// `.astype(np.float32)` does (__init__.py:14), so paths are bit-identical to the reference run on the promoted values.
+template <int VT> struct ValT { static constexpr int bytes = (VT == 0) ? 4 : 2; };
+__device__ __forceinline__ float half_bits_to_float(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)h)); }
+template <int VT> __device__ __forceinline__ float ld_val(uint32_t a) {                 // one score
+    if (VT == 0) return lds32(a);
+    uint32_t h;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(h) : "r"(a));
+    return VT == 1 ? half_bits_to_float(h) : __uint_as_float(h << 16);
+}
+template <int VT> __device__ __forceinline__ float4 ld_val4(uint32_t a) {               // four consecutive frames of a row
+    if (VT == 0) return lds128(a);
+    uint32_t lo, hi;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
+    if (VT == 1) return make_float4(half_bits_to_float(lo & 0xffffu), half_bits_to_float(lo >> 16), half_bits_to_float(hi & 0xffffu), half_bits_to_float(hi >> 16));
+    return make_float4(__uint_as_float(lo << 16), __uint_as_float(lo & 0xffff0000u), __uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
 }
 __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w));
@@ -291,7 +309,7 @@ struct Fwd {
 //   * the tile values of group g+1 and all boundary values of the unit are fetched before they are needed;
 //   * the body is branch-free: a completed direction word is snapshotted with predicated moves and stored once,
 //     after the unit, so the four groups stay one basic block.
-template <int R, int TF, int UNIT, bool SKEW, bool DIAG>
+template <int R, int TF, int UNIT, bool SKEW, bool DIAG, int VT>
 __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint32_t tile_prev, uint32_t bin_addr, uint32_t bout_addr, int Y, int yl,
                                              bool lane0, bool lane31, float neg, int dxy, uint32_t* bits_row, int TXS,
                                              int y_lo, unsigned span)
@@ -310,18 +328,19 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
     // reads frame Y + k - l, which is tile position k - l of this tile, or 32 + k - l of the previous one while k < l.  One
     // compare + select per frame picks the base; the loads are scalar and run two frames ahead.
     const int lane = Y - yl;
-    const uint32_t curA = tile_addr - 4u * (uint32_t)lane, prevA = tile_prev + 4u * (uint32_t)(TF - lane);
+    constexpr int ES = ValT<VT>::bytes;
+    const uint32_t curA = tile_addr - (uint32_t)(ES * lane), prevA = tile_prev + (uint32_t)(ES * (TF - lane));
     float vq[2][R];
     if (SKEW) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const uint32_t a = (lane <= q) ? curA : prevA;
 #pragma unroll
-            for (int r = 0; r < R; ++r) vq[q][r] = lds32(a + q * 4 + r * (TF * 4));
+            for (int r = 0; r < R; ++r) vq[q][r] = ld_val<VT>(a + q * ES + r * (TF * ES));
         }
     } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) vn[r] = lds128(tile_addr + r * (TF * 4));
+        for (int r = 0; r < R; ++r) vn[r] = ld_val4<VT>(tile_addr + r * (TF * ES));
     }
     uint32_t wdone[R];                                                // the word this lane completes inside this unit, if any
 #pragma unroll
@@ -335,7 +354,7 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
             for (int r = 0; r < R; ++r) v[r] = vn[r];
             if (g + 1 < NG) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) vn[r] = lds128(tile_addr + r * (TF * 4) + (g + 1) * 16);
+                for (int r = 0; r < R; ++r) vn[r] = ld_val4<VT>(tile_addr + r * (TF * ES) + (g + 1) * 4 * ES);
             }
         }
         // row above us at frames Y+4g-1 .. Y+4g+2 (skewed: slots Y+4g+30 .. Y+4g+33, i.e. .zw of the previous load, .xy of this one)
@@ -376,7 +395,7 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
             if (SKEW && kk + 2 < UNIT) {
                 const uint32_t a = (lane <= kk + 2) ? curA : prevA;
 #pragma unroll
-                for (int r = 0; r < R; ++r) vq[kk & 1][r] = lds32(a + (kk + 2) * 4 + r * (TF * 4));
+                for (int r = 0; r < R; ++r) vq[kk & 1][r] = ld_val<VT>(a + (kk + 2) * ES + r * (TF * ES));
             }
         }
         if (lane31) sts128(bout_addr + (((Y + 4 * g) & (kRing - 1)) << 2), o4[0], o4[1], o4[2], o4[3]);
@@ -538,14 +557,15 @@ __device__ __forceinline__ void backtrack_walk(const uint32_t* bits, int TXS, in
 // ------------------------------------------------------------------ the kernel
 // NWMAX bounds the compute warps of an instance (4 -> 256 threads, 8 -> 512 threads).  MINB = 2 holds an instance to 128
 // registers so two CTAs share an SM (throughput regime); MINB = 1 lets an utterance that owns its SM use up to 255.
-template <int R, int TF, bool SKEW, int NWMAX, int MINB, bool CL = false>
+template <int R, int TF, bool SKEW, int NWMAX, int MINB, bool CL = false, int VT = 0>
 __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasParams p, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int RW = 32 * R;
     // hand-off granularity between warps: a whole 32-frame tile when an utterance owns its SM (fewer flag/barrier round trips per
     // frame), 16 frames in the register-capped throughput instances
     constexpr int UNIT = (MINB == 1 && TF == 32) ? 32 : (TF < 16 ? TF : 16);
-    constexpr int LANE_STRIDE = R * TF * 4 + (SKEW ? 0 : kLanePad);   // skewed: dense TMA tiles, the scalar reads of lanes l and frames k - l hit 32 banks
+    constexpr int ES = ValT<VT>::bytes;                  // bytes per score
+    constexpr int LANE_STRIDE = R * TF * ES + (SKEW ? 0 : kLanePad);   // skewed: dense TMA tiles, the scalar reads of lanes l and frames k - l hit 32 banks
     constexpr int LAG31 = SKEW ? 31 * kSkewLag : 0;      // frames lane 31 trails lane 0
 
     extern __shared__ __align__(128) unsigned char smem[];
@@ -701,9 +721,10 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 }
             };
             if (active) {
-                const float* vrow = p.values + item * item_elems + (int64_t)x0 * Ty;
+                const unsigned char* vrow = reinterpret_cast<const unsigned char*>(p.values) + (item * item_elems + (int64_t)x0 * Ty) * ES;
                 const int band_hi0 = t_y - t_x + x0;               // last live frame of row i is band_hi0 + i
-                constexpr int CPR = TF / 4;                         // 16-byte chunks per row
+                constexpr int FPC = 16 / ES;                        // frames per 16-byte chunk
+                constexpr int CPR = TF / FPC;                       // 16-byte chunks per row
                 constexpr int RPI = 32 / CPR;                       // row segments per warp instruction
                 const int ck = lane % CPR, q0 = lane / CPR;
                 const int my_tiles = t_e - t_s;
@@ -719,33 +740,38 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                         // one 2-D box load per tile: all 32*R rows of this warp x TF frames (the host only picks this form for
                         // 16-byte aligned inputs); rows past t_x and frames past T_mel are fetched or zero-filled, never used
                         if (lane == 0) {
-                            mbar_expect_tx(full0 + 8 * stage, RW * TF * 4);
+                            mbar_expect_tx(full0 + 8 * stage, RW * TF * ES);
                             tma_load_2d(st, &tmap, t * TF, item * p.Tx + x0, full0 + 8 * stage);
                         }
                     } else if (p.aligned) {
                         // Loader lane = (16-byte chunk ck of a row, row group q0); it walks the owner lanes li = q0, q0+RPI, ...
                         // and their R rows, so one warp-wide LDGSTS.128 moves RPI whole row segments.
-                        const int f0 = t * TF + ck * 4;
+                        const int f0 = t * TF + ck * FPC;
                         for (int li = q0; li * R < nrows; li += RPI) {
                             const int f = f0;                                   // frame of this chunk
-                            const int lo = (x0 + li * R) & ~3;                  // chunks wholly above the diagonal are never read
+                            const int lo = (x0 + li * R) & ~(FPC - 1);          // chunks wholly above the diagonal are never read
                             const uint32_t d = st + li * LANE_STRIDE + ck * 16;
-                            const float* src = vrow + (int64_t)(li * R) * Ty + f;
+                            const unsigned char* src = vrow + ((int64_t)(li * R) * Ty + f) * ES;
 #pragma unroll
                             for (int r = 0; r < R; ++r) {
                                 const int i = li * R + r;
-                                if (i < nrows && f >= lo && f <= band_hi0 + i && f + 4 <= Ty)
-                                    cp_async16(d + r * (TF * 4), src + (int64_t)r * Ty);
+                                if (i < nrows && f >= lo && f <= band_hi0 + i && f + FPC <= Ty)
+                                    cp_async16(d + r * (TF * ES), src + (int64_t)r * Ty * ES);
                             }
                         }
                         cp_async_arrive(full0 + 8 * stage);
                     } else {
-                        // unaligned base pointer or T_mel % 4 != 0: plain 4-byte loads, same placement
-                        float* sp = reinterpret_cast<float*>(smem + L.off_ring + (size_t)(w * NS + stage) * L.stage_bytes);
+                        // unaligned base pointer or row pitch: plain element loads, same placement
+                        unsigned char* sp = smem + L.off_ring + (size_t)(w * NS + stage) * L.stage_bytes;
                         for (int idx = lane; idx < nrows * TF; idx += 32) {
                             const int i = idx / TF, fl = idx - i * TF, li = i / R;
                             const int f = t * TF + fl;
-                            if (f >= 0 && f <= band_hi0 + i && f < Ty) sp[(i * (TF * 4) + li * kLanePad) / 4 + fl] = vrow[(int64_t)i * Ty + f];
+                            if (f >= 0 && f <= band_hi0 + i && f < Ty) {
+                                const size_t so = (size_t)i * (TF * ES) + (size_t)li * kLanePad + (size_t)fl * ES;
+                                const size_t go = ((int64_t)i * Ty + f) * ES;
+                                if (ES == 4) *reinterpret_cast<float*>(sp + so) = *reinterpret_cast<const float*>(vrow + go);
+                                else *reinterpret_cast<unsigned short*>(sp + so) = *reinterpret_cast<const unsigned short*>(vrow + go);
+                            }
                         }
                         mbar_arrive(full0 + 8 * stage);
                     }
@@ -840,14 +866,14 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 const int next_in = (has_in && !remote_in) ? ld_flag(in_tail) : kProgDone;
                 const int next_cons = has_consumer ? ld_flag(out_head) : kProgDone;
                 if (dbg_on) c2 = clock64();
-                const uint32_t tile_addr = ring_a + stage * L.stage_bytes + lane * LANE_STRIDE + fin * 4;
+                const uint32_t tile_addr = ring_a + stage * L.stage_bytes + lane * LANE_STRIDE + fin * ES;
                 const uint32_t tile_prev = (SKEW && y > y_start) ? ring_a + prev_stage * L.stage_bytes + lane * LANE_STRIDE : tile_addr;
                 const int yl = y - lag;
                 if (y < diag_end)
-                    forward_unit<R, TF, UNIT, SKEW, true>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
+                    forward_unit<R, TF, UNIT, SKEW, true, VT>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
                                                           xl0 - yl, bits_row, TXS, y_start, (unsigned)span);
                 else
-                    forward_unit<R, TF, UNIT, SKEW, false>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
+                    forward_unit<R, TF, UNIT, SKEW, false, VT>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
                                                            0, bits_row, TXS, y_start, (unsigned)span);
                 seen_in = next_in;
                 seen_cons = next_cons;

@@ -43,15 +43,30 @@ def _workspace(device: torch.device, stream: int, b: int, tx: int, ty: int) -> t
     return ws
 
 
+_VALUE_DTYPE = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+
+
 def _prep_value(value: torch.Tensor) -> torch.Tensor:
+    """Contiguous scores in a dtype the kernels read directly: fp32, or fp16 / bf16 as they are (the kernel promotes
+    them on load, exactly like .astype(np.float32) in the reference, __init__.py:14); anything else is promoted here."""
     if value.dim() != 3:
         raise ValueError("value must be [b, t_x, t_y], got %s" % (tuple(value.shape),))
     if not value.is_cuda:
         raise RuntimeError("aligner_b200 runs on sm_100a only: value must be a CUDA tensor (no CPU fallback)")
     v = value.detach()
-    if v.dtype != torch.float32:
-        v = v.to(torch.float32)      # what .astype(np.float32) does in the reference (__init__.py:14)
+    if v.dtype not in _VALUE_DTYPE:
+        v = v.to(torch.float32)
     return v.contiguous()
+
+
+def _launch(v: torch.Tensor, args_after_value: tuple) -> None:
+    """alb200_mas_device_ex on v; a half-precision tensor the library has no native kernel shape for
+    (ALB200_E_UNSUPPORTED) is promoted to fp32 on the device and retried -- still no CPU anywhere."""
+    rc = _lib.lib.alb200_mas_device_ex(v.data_ptr(), _VALUE_DTYPE[v.dtype], *args_after_value)
+    if rc == _lib.E_UNSUPPORTED and v.dtype != torch.float32:
+        v32 = v.to(torch.float32)
+        rc = _lib.lib.alb200_mas_device_ex(v32.data_ptr(), _lib.F32, *args_after_value)
+    _lib.check(rc)
 
 
 def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, return_durations: bool = False):
@@ -87,10 +102,9 @@ def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, return_durations: b
         ws = _workspace(v.device, stream, b, tx, ty)
         m = mask.detach()
         sb, sx, sy = m.stride()
-        _lib.check(_lib.lib.alb200_mas_device_masked(
-            v.data_ptr(), m.data_ptr(), _MASK_DTYPE[m.dtype], sb, sx, sy,
-            path.data_ptr(), esize, one, 1, None, dur.data_ptr() if dur is not None else None, None,
-            b, tx, ty, -1e9, ws.data_ptr(), ws.numel(), stream))
+        _launch(v, (None, None, m.data_ptr(), _MASK_DTYPE[m.dtype], sb, sx, sy, None,
+                    path.data_ptr(), esize, one, 1, None, dur.data_ptr() if dur is not None else None, None,
+                    b, tx, ty, -1e9, ws.data_ptr(), ws.numel(), stream))
     return (path, dur) if return_durations else path
 
 
@@ -128,11 +142,10 @@ def maximum_path_lengths(value: torch.Tensor, x_lengths: torch.Tensor, y_lengths
                 order = order.to(device=v.device, dtype=torch.int32).contiguous()
                 if order.numel() != b:
                     raise ValueError("order must hold a permutation of range(b)")
-            _lib.check(_lib.lib.alb200_mas_device_ordered(
-                v.data_ptr(), xl.data_ptr(), yl.data_ptr(), order.data_ptr() if order is not None else None,
-                path.data_ptr() if dense else None, esize, one, 1,
-                ftok.data_ptr() if ftok is not None else None, dur.data_ptr() if dur is not None else None,
-                b, tx, ty, max_neg_val, ws.data_ptr(), ws.numel(), stream))
+            _launch(v, (xl.data_ptr(), yl.data_ptr(), None, 0, 0, 0, 0, order.data_ptr() if order is not None else None,
+                        path.data_ptr() if dense else None, esize, one, 1,
+                        ftok.data_ptr() if ftok is not None else None, dur.data_ptr() if dur is not None else None, None,
+                        b, tx, ty, max_neg_val, ws.data_ptr(), ws.numel(), stream))
         if dense:
             out["path"] = path
         if dur is not None:

@@ -86,6 +86,23 @@ int alb200_mas_device_ordered(const float *values, const int32_t *t_xs, const in
                               int b, int tx, int ty, float max_neg_val,
                               void *workspace, size_t workspace_bytes, void *stream);
 
+/* The general device entry: every option of the three entries around it, plus the score element type.
+ *   value_dtype  ALB200_F32, ALB200_F16 or ALB200_BF16.  Half-precision scores are promoted to fp32 as they are loaded,
+ *                which is exactly the reference's `.astype(np.float32)` (monotonic_align/__init__.py:14): the path is
+ *                bit-identical to the reference run on the promoted values, and the kernel reads 2 instead of 4 bytes
+ *                per cell.  Native half-precision kernels exist for the shapes the host heuristics
+ *                pick (<= 4 rows per lane in the latency regime, the throughput regime); otherwise the call returns
+ *                ALB200_E_UNSUPPORTED and the caller promotes to fp32 on the device first (the Python layer does).
+ *   lengths      either (t_xs, t_ys) or mask (+ strides in elements), as in alb200_mas_device / _masked.
+ *   order        optional, as in alb200_mas_device_ordered. */
+int alb200_mas_device_ex(const void *values, int value_dtype, const int32_t *t_xs, const int32_t *t_ys,
+                         const void *mask, int mask_dtype, int64_t mask_stride_b, int64_t mask_stride_x, int64_t mask_stride_y,
+                         const int32_t *order,
+                         void *paths, int path_elem_size, uint64_t path_one, int zero_fill,
+                         int32_t *frame_tok, int32_t *durations, int32_t *lens_out,
+                         int b, int tx, int ty, float max_neg_val,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
 /* Same, with the lengths derived inside the kernel from a [b,tx,ty] mask the way
  * the reference's Python layer does (monotonic_align/__init__.py:18-19):
  *   t_x = sum_x mask[b, x, 0],  t_y = sum_y mask[b, 0, y], truncated to int32.

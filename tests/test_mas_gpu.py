@@ -84,6 +84,43 @@ def test_differential_small(ma, monkeypatch, force, kind):
         check_against_oracle(ma, values, t_x, t_y)
 
 
+# ------------------------------------------------------------------ fp16 / bf16 scores read natively
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape,native", [((8, 150, 400), True),      # latency regime, skewed/TMA form, 2 rows per lane
+                                          ((5, 40, 96), True),        # one compute warp
+                                          ((3, 500, 640), True),      # 4 rows per lane
+                                          ((400, 90, 240), True),     # throughput regime, lock-step 16-frame tiles
+                                          ((400, 90, 243), True),     # ... unaligned rows: element loader
+                                          ((300, 600, 800), True),    # ... 8 rows per lane
+                                          ((6, 150, 403), False),     # latency regime + unaligned rows: promoted on the device
+                                          ((4, 700, 900), False)])    # latency regime, > 4 rows per lane: promoted on the device
+def test_half_precision_scores(ma, dtype, shape, native):
+    rng = np.random.default_rng(abs(hash((str(dtype), shape))) % (2 ** 31))
+    b, tx, ty = shape
+    v = torch.from_numpy(make_values(rng, "gauss", shape)).cuda().to(dtype)
+    t_x, t_y = random_lengths(rng, b, tx, ty)
+    xl, yl = torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda()
+    want = oracle_paths(v.float().cpu().numpy(), t_x, t_y)          # the reference promotes with .astype(np.float32): exact
+    out = ma.maximum_path_lengths(v, xl, yl, out_dtype=torch.int32, return_durations=True)
+    assert np.array_equal(out["path"].cpu().numpy(), want)
+    assert np.array_equal(out["durations"].cpu().numpy(), want.sum(-1))
+    # the public API with a mask, result dtype = result_type(value, mask)
+    mask = torch.from_numpy(prefix_mask_np(t_x, t_y, tx, ty)).cuda().to(dtype)
+    got = ma.maximum_path(v, mask)
+    assert got.dtype == dtype and np.array_equal(got.float().cpu().numpy(), want.astype(np.float32))
+    # is the native kernel really taken (no promotion pass)?
+    path = torch.empty(shape, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    ws = ma._workspace(v.device, stream, b, tx, ty)
+    rc = _lib.lib.alb200_mas_device_ex(v.data_ptr(), _lib.F16 if dtype == torch.float16 else _lib.BF16, xl.data_ptr(), yl.data_ptr(),
+                                       None, 0, 0, 0, 0, None, path.data_ptr(), 4, 1, 1, None, None, None, b, tx, ty, -1e9,
+                                       ws.data_ptr(), ws.numel(), stream)
+    torch.cuda.synchronize()
+    assert rc == (0 if native else _lib.E_UNSUPPORTED)
+    if native:
+        assert np.array_equal(path.cpu().numpy(), want)
+
+
 def test_processing_order_does_not_change_results(ma):
     """alb200_mas_device_ordered: any permutation (and the built-in longest-first order) gives the batch-order result."""
     rng = np.random.default_rng(11)
