@@ -6,11 +6,15 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import aligner_b200.monotonic_align as ma
 import aligner_b200.neg_cent as nc
 rng = np.random.default_rng(0)
-for force in (None, "2,32,2,1,1", "3,16,2,0,0"):
+CASES = [(None, 5, 150, 260, torch.float32), ("2,32,2,1,1", 5, 150, 260, torch.float32), ("3,16,2,0,0", 5, 150, 260, torch.float32),
+         ("2,32,2,0,1,2", 3, 300, 420, torch.float32),        # cluster of 2 CTAs per utterance
+         ("1,32,3,0,1,4", 2, 500, 520, torch.float32),        # cluster of 4
+         (None, 4, 150, 264, torch.bfloat16), (None, 200, 70, 136, torch.float16),     # native half-precision scores: skewed/TMA and throughput forms
+         (None, 200, 70, 133, torch.float32)]                 # throughput regime, unaligned rows
+for force, b, tx, ty, dt in CASES:
     if force: os.environ["ALB200_FORCE"] = force
     else: os.environ.pop("ALB200_FORCE", None)
-    b, tx, ty = 5, 150, 260
-    v = torch.randn(b, tx, ty, device="cuda")
+    v = torch.randn(b, tx, ty, device="cuda").to(dt)
     t_x = rng.integers(1, tx + 1, b).astype(np.int32); t_y = np.array([rng.integers(t_x[i], ty + 1) for i in range(b)], np.int32)
     out = ma.maximum_path_lengths(v, torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda(), return_durations=True, return_frame_tokens=True)
     torch.cuda.synchronize()
