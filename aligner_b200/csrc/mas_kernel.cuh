@@ -319,10 +319,11 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
     // Skewed form: lane l is l frames behind lane 0, so lane 31 of the warp above us finishes frame f at ITS step f + 31.  The
     // boundary ring is indexed by the producer's step (aligned 128-bit stores); frame f sits in slot f + 31.
     float4 bin[NG];
+    // Y is a multiple of UNIT and the ring a multiple of 32 slots: the unit's slots never wrap, one base + immediates
+    const uint32_t bin_base = bin_addr + (((Y + (SKEW ? 32 : 0)) & (kRing - 1)) << 2);
+    const uint32_t bout_base = bout_addr + ((Y & (kRing - 1)) << 2);
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        bin[g] = lds128(bin_addr + (((Y + 4 * g + (SKEW ? 32 : 0)) & (kRing - 1)) << 2));
-    }
+    for (int g = 0; g < NG; ++g) bin[g] = lds128(bin_base + 16 * g);
     float4 vn[R];
     // Skewed form: the tiles in shared memory are NOT skewed (same 128-bit asynchronous copies as the lock-step form); lane l
     // reads frame Y + k - l, which is tile position k - l of this tile, or 32 + k - l of the previous one while k < l.  One
@@ -398,7 +399,7 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
                 for (int r = 0; r < R; ++r) vq[kk & 1][r] = ld_val<VT>(a + (kk + 2) * ES + r * (TF * ES));
             }
         }
-        if (lane31) sts128(bout_addr + (((Y + 4 * g) & (kRing - 1)) << 2), o4[0], o4[1], o4[2], o4[3]);
+        if (lane31) sts128(bout_base + 16 * g, o4[0], o4[1], o4[2], o4[3]);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             S.wbits[r] = __funnelshift_r(S.wbits[r], hb[r], 4);

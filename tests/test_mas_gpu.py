@@ -161,6 +161,13 @@ def test_cluster_mode_is_the_default_for_long_text(ma):
     t_x, t_y = random_lengths(rng, b, tx, ty)                          # short items leave whole CTAs of a cluster idle
     t_x[0], t_y[0] = 7, 9
     check_against_oracle(ma, values, t_x, t_y)
+    # the reference API (lengths from the mask, in every CTA of the cluster) and an explicit processing order
+    want = oracle_paths(values, t_x, t_y)
+    v = torch.from_numpy(values).cuda()
+    got = ma.maximum_path(v, torch.from_numpy(prefix_mask_np(t_x, t_y, tx, ty)).cuda())
+    assert np.array_equal(got.cpu().numpy(), want.astype(np.float32))
+    out = ma.maximum_path_lengths(v, torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda(), out_dtype=torch.int32, order="lpt")
+    assert np.array_equal(out["path"].cpu().numpy(), want)
     assert "cluster=1" in _lib.describe(148, tx, ty)                   # not when the clusters would not all be resident
 
 
@@ -308,7 +315,7 @@ def test_max_neg_val_keyword(ma):
 def test_host_maximum_path_c(ma):
     from monotonic_align.monotonic_align.core import maximum_path_c
     rng = np.random.default_rng(35)
-    for (b, tx, ty) in [(1, 1, 1), (7, 50, 200), (64, 200, 1000), (40, 97, 333)]:
+    for (b, tx, ty) in [(1, 1, 1), (7, 50, 200), (64, 200, 1000), (40, 97, 333), (5, 700, 1204)]:      # the last one runs as clusters of 3 CTAs
         values = make_values(rng, "gauss", (b, tx, ty))
         t_x, t_y = random_lengths(rng, b, tx, ty)
         if b > 3:
