@@ -9,7 +9,7 @@ Everything computes in hand-written CUDA reached through a C ABI
 (include/aligner_b200.h, libaligner_b200.so); there is no CPU fallback.
 """
 from . import _lib  # noqa: F401  (raises ImportError if the CUDA library is not built)
-from .monotonic_align import maximum_path, maximum_path_c, maximum_path_lengths  # noqa: F401
+from .monotonic_align import maximum_path, maximum_path_c, maximum_path_lengths, maximum_path_vits  # noqa: F401
 from .sharding import balance_shards, lpt_order  # noqa: F401  (multi-GPU / ragged-batch planning, SURVEY.md 8e)
 
 __version__ = "0.1.0"

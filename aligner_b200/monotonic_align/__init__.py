@@ -14,7 +14,7 @@ import torch
 from .. import _lib
 from .monotonic_align.core import maximum_path_c  # noqa: F401  (same import the reference does, __init__.py:3)
 
-__all__ = ["maximum_path", "maximum_path_lengths", "maximum_path_c", "check_status"]
+__all__ = ["maximum_path", "maximum_path_vits", "maximum_path_lengths", "maximum_path_c", "check_status"]
 
 # bit pattern of 1 in every dtype torch.result_type can produce here
 _ONE = {
@@ -106,6 +106,18 @@ def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, return_durations: b
                     path.data_ptr(), esize, one, 1, None, dur.data_ptr() if dur is not None else None, None,
                     b, tx, ty, -1e9, ws.data_ptr(), ws.numel(), stream))
     return (path, dur) if return_durations else path
+
+
+def maximum_path_vits(neg_cent: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """VITS-layout entry: ``neg_cent`` and ``mask`` are ``[b, t_mel, t_text]`` as in VITS'
+    ``monotonic_align.maximum_path`` (its core indexes ``value[y, x]``), the result has the same layout.
+
+    The search itself is layout-agnostic; this entry hands the kernel the ``[b, t_text, t_mel]`` view: the mask is read
+    through its strides (no copy), the scores are made contiguous by one device transpose (the kernels stream along the
+    mel axis), and the returned path is the transposed view of the kernel's output (no copy)."""
+    if neg_cent.dim() != 3 or mask.shape != neg_cent.shape:
+        raise ValueError("expected neg_cent and mask of shape [b, t_mel, t_text]")
+    return maximum_path(neg_cent.transpose(1, 2), mask.transpose(1, 2)).transpose(1, 2)
 
 
 def maximum_path_lengths(value: torch.Tensor, x_lengths: torch.Tensor, y_lengths: torch.Tensor, *,

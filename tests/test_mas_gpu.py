@@ -84,6 +84,20 @@ def test_differential_small(ma, monkeypatch, force, kind):
         check_against_oracle(ma, values, t_x, t_y)
 
 
+def test_vits_layout_entry(ma):
+    """[b, t_mel, t_text] in and out, as VITS calls it; same search (its core indexes value[y, x])."""
+    rng = np.random.default_rng(21)
+    b, tx, ty = 6, 70, 190
+    values = make_values(rng, "gauss", (b, tx, ty))
+    t_x, t_y = random_lengths(rng, b, tx, ty)
+    want = oracle_paths(values, t_x, t_y)
+    v = torch.from_numpy(np.ascontiguousarray(values.transpose(0, 2, 1))).cuda()                    # [b, t_mel, t_text]
+    m = torch.from_numpy(np.ascontiguousarray(prefix_mask_np(t_x, t_y, tx, ty).transpose(0, 2, 1))).cuda()
+    got = ma.maximum_path_vits(v, m)
+    assert got.shape == v.shape and got.dtype == v.dtype
+    assert np.array_equal(got.cpu().numpy(), want.transpose(0, 2, 1).astype(np.float32))
+
+
 # ------------------------------------------------------------------ fp16 / bf16 scores read natively (SURVEY.md 8f-4)
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("shape,native", [((8, 150, 400), True),      # latency regime, skewed/TMA form, 2 rows per lane
