@@ -17,6 +17,7 @@ E_INVALID, E_UNSUPPORTED, E_CUDA, E_LENGTHS, E_NO_DEVICE = -1, -2, -3, -4, -5
 
 # mask element types (ALB200_* in the header)
 F32, F16, BF16, F64, U8, I8, I16, I32, I64 = range(9)
+LAYOUT_VITS = 0x100   # OR into the value dtype of alb200_mas_device_ex: scores and path are [b, t_mel, t_text]
 
 # every symbol include/aligner_b200.h declares (tests check the export list against the header)
 SYMBOLS = (

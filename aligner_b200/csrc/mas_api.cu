@@ -85,6 +85,9 @@ static const KEntry g_kernels[] = {
     { 2, 16, 0, 4, 2, mas_kernel<2, 16, false, 4, 2, false, VT>, VT }, { 4, 16, 0, 4, 2, mas_kernel<4, 16, false, 4, 2, false, VT>, VT }, \
     { 8, 16, 0, 4, 2, mas_kernel<8, 16, false, 4, 2, false, VT>, VT }, { 16, 16, 0, 4, 2, mas_kernel<16, 16, false, 4, 2, false, VT>, VT }
     ALB_KH(1), ALB_KH(2),
+    // VITS layout (scores and path stored [b, t_mel, t_text]): skewed/TMA form, fp32, skew code 3
+    { 1, 32, 3, 4, 1, mas_kernel<1, 32, true, 4, 1, false, 0, true>, 0 }, { 2, 32, 3, 4, 1, mas_kernel<2, 32, true, 4, 1, false, 0, true>, 0 },
+    { 3, 32, 3, 4, 1, mas_kernel<3, 32, true, 4, 1, false, 0, true>, 0 }, { 4, 32, 3, 4, 1, mas_kernel<4, 32, true, 4, 1, false, 0, true>, 0 },
 };
 static KernelFn find_kernel(int R, int TF, int skew, int nw, int minb, int vt)
 {
@@ -106,7 +109,7 @@ struct Config {
 //   throughput regime (b > #SM): 4 rows per lane, and the smallest ring (>= 2 stages) that lets the 128-register
 //                    instances reach their register-limited occupancy (8 / compute-warps CTAs per SM), so that about 8
 //                    compute warps per SM hide each other's latency and one item's backtrack overlaps others' streaming.
-static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, int vt, Config* c)
+static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, int vt, int vl, Config* c)
 {
     const bool latency = b <= di.sms;
     int R, NW;
@@ -134,7 +137,7 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     // CTA, boundary rows handed over through distributed shared memory).  Only when every cluster gets its own SMs.
     int NC = 1;
     if (f_nc > 0) NC = f_nc;
-    else if (latency && aligned && tx > 512 && fr == 0 && f_skew != 0 && vt == 0) {
+    else if (latency && aligned && tx > 512 && fr == 0 && f_skew != 0 && vt == 0 && !vl) {
         const int want = (tx + 255) / 256;
         if (want <= 8 && (int64_t)b * want <= di.sms) NC = want;
     }
@@ -153,6 +156,7 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     // (profiles/r01_skew_sweep.json): faster or equal wherever an utterance owns its SM and has <= 4 rows per lane.
     int want_skew = f_skew >= 0 ? f_skew : ((latency && R <= 4) ? 1 : 0);
     if (NC > 1) want_skew = 1;
+    if (vl && (NC > 1 || vt != 0)) return fail(ALB200_E_UNSUPPORTED, "the [t_mel, t_text] layout has fp32 single-CTA kernels only%s", "");
     if (!aligned || R > 8) want_skew = 0;                      // its tiles come in by TMA: 16-byte aligned rows, <= 256 rows per box
     auto try_fit = [&](int tf, int ns, int bs, int budget) -> bool {
         if (want_skew && tf != 32) return false;
@@ -192,7 +196,8 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     if (!latency && !c->skew)
         for (const KEntry& k : g_kernels)
             if (k.R == R && k.TF == best_tf && k.skew == 0 && NW <= k.nwmax && k.minb == 2 && k.vt == vt) { c->fn = k.fn; break; }
-    if (!c->fn) c->fn = find_kernel(R, best_tf, NC > 1 ? 2 : c->skew, NW, latency ? 1 : 2, vt);
+    if (vl && !c->skew) return fail(ALB200_E_UNSUPPORTED, "the [t_mel, t_text] layout needs the skewed/TMA form (latency regime, <= 4 rows per lane, 16-byte aligned rows)%s", "");
+    if (!c->fn) c->fn = find_kernel(R, best_tf, vl ? 3 : (NC > 1 ? 2 : c->skew), NW, latency ? 1 : 2, vt);
     if (!c->fn) return fail(ALB200_E_UNSUPPORTED, "no kernel instance for R=%s%lld TF=%lld (score type %lld)", "", R, best_tf, vt);
     SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur, want_skew, NC, vt ? 2 : 4);
     c->smem = L.total;
@@ -207,15 +212,15 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
 }
 
 // select_config_uncached costs a few driver calls; remember the answers (per thread, tiny table).
-struct CfgKey { int dev, latency, tx, ty, dur, aligned, bclass, vt; char env[48]; };
-static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, Config* c, int vt = 0)
+struct CfgKey { int dev, latency, tx, ty, dur, aligned, bclass, vt, vl; char env[48]; };
+static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, Config* c, int vt = 0, int vl = 0)
 {
     static thread_local CfgKey keys[8];
     static thread_local Config vals[8];
     static thread_local int used = 0, next = 0;
     CfgKey k;
     memset(&k, 0, sizeof(k));
-    k.dev = di.dev; k.latency = b <= di.sms; k.tx = tx; k.ty = ty; k.dur = want_dur; k.aligned = aligned; k.vt = vt;
+    k.dev = di.dev; k.latency = b <= di.sms; k.tx = tx; k.ty = ty; k.dur = want_dur; k.aligned = aligned; k.vt = vt; k.vl = vl;
     k.bclass = (k.latency && tx > 512) ? b : 0;                 // the cluster decision depends on how many clusters fit
     if (const char* f = getenv("ALB200_FORCE")) strncpy(k.env, f, sizeof(k.env) - 1);
     int hit = -1;
@@ -223,7 +228,7 @@ static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur
         if (memcmp(&keys[i], &k, sizeof(k)) == 0) { hit = i; break; }
     if (hit < 0) {
         Config fresh;
-        int rc = select_config_uncached(di, b, tx, ty, want_dur, aligned, vt, &fresh);
+        int rc = select_config_uncached(di, b, tx, ty, want_dur, aligned, vt, vl, &fresh);
         if (rc) return rc;
         hit = next; next = (next + 1) % 8; if (used < 8) ++used;
         keys[hit] = k; vals[hit] = fresh;
@@ -238,7 +243,7 @@ static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur
 // loader fetches one box per tile (cp.async.bulk.tensor).  Encoding is host-side arithmetic; the last few are remembered.
 typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int values_tensor_map(const void* values, int vt, int b, int tx, int ty, int box_rows, int box_frames, CUtensorMap* out)
+static int values_tensor_map(const void* values, int vt, int vl, int b, int tx, int ty, int box_rows, int box_frames, CUtensorMap* out)
 {
     static TmapEncodeFn enc = nullptr;
     if (!enc) {
@@ -248,20 +253,22 @@ static int values_tensor_map(const void* values, int vt, int b, int tx, int ty, 
         if (!fn || q != cudaDriverEntryPointSuccess) return fail(ALB200_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver%s", "");
         enc = reinterpret_cast<TmapEncodeFn>(fn);
     }
-    struct Key { const void* v; int b, tx, ty, br, bf, vt; };
+    struct Key { const void* v; int b, tx, ty, br, bf, vt, vl; };
     static thread_local Key keys[16];
     static thread_local CUtensorMap maps[16];
     static thread_local int used = 0, next = 0;
-    const Key k = { values, b, tx, ty, box_rows, box_frames, vt };
+    const Key k = { values, b, tx, ty, box_rows, box_frames, vt, vl };
     for (int i = 0; i < used; ++i)
-        if (keys[i].v == k.v && keys[i].b == b && keys[i].tx == tx && keys[i].ty == ty && keys[i].br == box_rows && keys[i].bf == box_frames && keys[i].vt == vt) {
+        if (keys[i].v == k.v && keys[i].b == b && keys[i].tx == tx && keys[i].ty == ty && keys[i].br == box_rows && keys[i].bf == box_frames && keys[i].vt == vt && keys[i].vl == vl) {
             *out = maps[i];
             return 0;
         }
     if ((int64_t)b * tx > 0x7fffffffLL) return fail(ALB200_E_UNSUPPORTED, "b * t_x = %s%lld rows exceed the tensor-map coordinate range", "", (long long)b * tx);
-    cuuint64_t dims[2] = { (cuuint64_t)ty, (cuuint64_t)b * (cuuint64_t)tx };
-    cuuint64_t strides[1] = { (cuuint64_t)ty * (vt ? 2 : 4) };
-    cuuint32_t box[2] = { (cuuint32_t)box_frames, (cuuint32_t)box_rows }, es[2] = { 1, 1 };
+    if ((int64_t)b * ty > 0x7fffffffLL) return fail(ALB200_E_UNSUPPORTED, "b * t_y = %s%lld rows exceed the tensor-map coordinate range", "", (long long)b * ty);
+    // [b*t_x, t_y] with a (tokens x frames) box -- or, VITS layout, [b*t_y, t_x] with the same box seen the other way round
+    cuuint64_t dims[2] = { (cuuint64_t)(vl ? tx : ty), (cuuint64_t)b * (cuuint64_t)(vl ? ty : tx) };
+    cuuint64_t strides[1] = { (cuuint64_t)(vl ? tx : ty) * (vt ? 2 : 4) };
+    cuuint32_t box[2] = { (cuuint32_t)(vl ? box_rows : box_frames), (cuuint32_t)(vl ? box_frames : box_rows) }, es[2] = { 1, 1 };
     const CUtensorMapDataType dt = vt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (vt == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
     CUresult r = enc(out, dt, 2, const_cast<void*>(values), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -279,7 +286,7 @@ static size_t ws_bytes_for(const Config& c)
 static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_ys, const void* mask, int mask_dtype,
                       int64_t msb, int64_t msx, int64_t msy, void* paths, int esize, uint64_t one, int zero_fill,
                       int32_t* frame_tok, int32_t* durations, int32_t* lens_out, int b, int tx, int ty, float neg,
-                      void* workspace, size_t workspace_bytes, cudaStream_t stream, const int32_t* order = nullptr, int vt = 0)
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream, const int32_t* order = nullptr, int vt = 0, int vl = 0)
 {
     if (!values || b < 0 || tx <= 0 || ty <= 0) return fail(ALB200_E_INVALID, "null values or non-positive shape%s", "");
     if (!mask && (!t_xs || !t_ys)) return fail(ALB200_E_INVALID, "need lengths or a mask%s", "");
@@ -293,9 +300,9 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
     if (rc) return rc;
     Config c;
     if (vt < 0 || vt > 2) return fail(ALB200_E_INVALID, "unknown score dtype %s%lld", "", vt);
-    bool aligned = (reinterpret_cast<uintptr_t>(values) & 15) == 0 && ((int64_t)ty * (vt ? 2 : 4)) % 16 == 0;
+    bool aligned = (reinterpret_cast<uintptr_t>(values) & 15) == 0 && ((int64_t)(vl ? tx : ty) * (vt ? 2 : 4)) % 16 == 0;
     if (getenv("ALB200_FORCE_UNALIGNED")) aligned = false;
-    rc = select_config(di, b, tx, ty, durations != nullptr, aligned, &c, vt);
+    rc = select_config(di, b, tx, ty, durations != nullptr, aligned, &c, vt, vl);
     if (rc) return rc;
     if (workspace_bytes < ws_bytes_for(c))
         return fail(ALB200_E_INVALID, "workspace too small: %s%lld < %lld bytes", "", (long long)workspace_bytes, (long long)ws_bytes_for(c));
@@ -318,7 +325,7 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (c.skew) {
-        rc = values_tensor_map(values, vt, b, tx, ty, 32 * c.R, c.TF, &tmap);
+        rc = values_tensor_map(values, vt, vl, b, tx, ty, 32 * c.R, c.TF, &tmap);
         if (rc) return rc;
     }
     p.neg = neg;
@@ -446,6 +453,8 @@ int alb200_mas_device_ex(const void* values, int value_dtype, const int32_t* t_x
                          int zero_fill, int32_t* frame_tok, int32_t* durations, int32_t* lens_out, int b, int tx, int ty, float max_neg_val,
                          void* workspace, size_t workspace_bytes, void* stream)
 {
+    const int vl = (value_dtype & ALB200_LAYOUT_VITS) ? 1 : 0;
+    value_dtype &= ~ALB200_LAYOUT_VITS;
     int vt;
     switch (value_dtype) {
         case ALB200_F32: vt = 0; break;
@@ -454,7 +463,7 @@ int alb200_mas_device_ex(const void* values, int value_dtype, const int32_t* t_x
         default: return fail(ALB200_E_INVALID, "score dtype %s%lld is not fp32, fp16 or bf16", "", value_dtype);
     }
     return launch_mas(values, t_xs, t_ys, mask, mask_dtype, msb, msx, msy, paths, path_elem_size, path_one, zero_fill, frame_tok,
-                      durations, lens_out, b, tx, ty, max_neg_val, workspace, workspace_bytes, (cudaStream_t)stream, order, vt);
+                      durations, lens_out, b, tx, ty, max_neg_val, workspace, workspace_bytes, (cudaStream_t)stream, order, vt, vl);
 }
 
 int alb200_mas_device_masked(const float* values, const void* mask, int mask_dtype, int64_t msb, int64_t msx, int64_t msy,

@@ -309,7 +309,7 @@ struct Fwd {
 //   * the tile values of group g+1 and all boundary values of the unit are fetched before they are needed;
 //   * the body is branch-free: a completed direction word is snapshotted with predicated moves and stored once,
 //     after the unit, so the four groups stay one basic block.
-template <int R, int TF, int UNIT, bool SKEW, bool DIAG, int VT>
+template <int R, int TF, int UNIT, bool SKEW, bool DIAG, int VT, bool VL>
 __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint32_t tile_prev, uint32_t bin_addr, uint32_t bout_addr, int Y, int yl,
                                              bool lane0, bool lane31, float neg, int dxy, uint32_t* bits_row, int TXS,
                                              int y_lo, unsigned span)
@@ -330,14 +330,19 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
     // compare + select per frame picks the base; the loads are scalar and run two frames ahead.
     const int lane = Y - yl;
     constexpr int ES = ValT<VT>::bytes;
-    const uint32_t curA = tile_addr - (uint32_t)(ES * lane), prevA = tile_prev + (uint32_t)(ES * (TF - lane));
+    // VL (VITS layout, scores stored [t_mel][t_text]): a tile is [TF frames][32*R tokens], so consecutive frames of a token
+    // are one tile row apart and a lane's R tokens are adjacent; otherwise [32*R tokens][TF frames].
+    constexpr int FSTR = VL ? 32 * R * ES : ES;              // bytes between consecutive frames of one token
+    constexpr int RSTR = VL ? ES : TF * ES;                  // bytes between a lane's consecutive tokens
+    static_assert(!VL || SKEW, "the VITS layout exists for the skewed/TMA form only");
+    const uint32_t curA = tile_addr - (uint32_t)(FSTR * lane), prevA = tile_prev + (uint32_t)(FSTR * (TF - lane));
     float vq[2][R];
     if (SKEW) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const uint32_t a = (lane <= q) ? curA : prevA;
 #pragma unroll
-            for (int r = 0; r < R; ++r) vq[q][r] = ld_val<VT>(a + q * ES + r * (TF * ES));
+            for (int r = 0; r < R; ++r) vq[q][r] = ld_val<VT>(a + q * FSTR + r * RSTR);
         }
     } else {
 #pragma unroll
@@ -396,7 +401,7 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
             if (SKEW && kk + 2 < UNIT) {
                 const uint32_t a = (lane <= kk + 2) ? curA : prevA;
 #pragma unroll
-                for (int r = 0; r < R; ++r) vq[kk & 1][r] = ld_val<VT>(a + (kk + 2) * ES + r * (TF * ES));
+                for (int r = 0; r < R; ++r) vq[kk & 1][r] = ld_val<VT>(a + (kk + 2) * FSTR + r * RSTR);
             }
         }
         if (lane31) sts128(bout_base + 16 * g, o4[0], o4[1], o4[2], o4[3]);
@@ -558,7 +563,7 @@ __device__ __forceinline__ void backtrack_walk(const uint32_t* bits, int TXS, in
 // ------------------------------------------------------------------ the kernel
 // NWMAX bounds the compute warps of an instance (4 -> 256 threads, 8 -> 512 threads).  MINB = 2 holds an instance to 128
 // registers so two CTAs share an SM (throughput regime); MINB = 1 lets an utterance that owns its SM use up to 255.
-template <int R, int TF, bool SKEW, int NWMAX, int MINB, bool CL = false, int VT = 0>
+template <int R, int TF, bool SKEW, int NWMAX, int MINB, bool CL = false, int VT = 0, bool VL = false>
 __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasParams p, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int RW = 32 * R;
@@ -742,7 +747,8 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                         // 16-byte aligned inputs); rows past t_x and frames past T_mel are fetched or zero-filled, never used
                         if (lane == 0) {
                             mbar_expect_tx(full0 + 8 * stage, RW * TF * ES);
-                            tma_load_2d(st, &tmap, t * TF, item * p.Tx + x0, full0 + 8 * stage);
+                            if (VL) tma_load_2d(st, &tmap, x0, item * Ty + t * TF, full0 + 8 * stage);      // box = RW tokens x TF frames of [b*t_mel, t_text]
+                            else tma_load_2d(st, &tmap, t * TF, item * p.Tx + x0, full0 + 8 * stage);
                         }
                     } else if (p.aligned) {
                         // Loader lane = (16-byte chunk ck of a row, row group q0); it walks the owner lanes li = q0, q0+RPI, ...
@@ -867,14 +873,15 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 const int next_in = (has_in && !remote_in) ? ld_flag(in_tail) : kProgDone;
                 const int next_cons = has_consumer ? ld_flag(out_head) : kProgDone;
                 if (dbg_on) c2 = clock64();
-                const uint32_t tile_addr = ring_a + stage * L.stage_bytes + lane * LANE_STRIDE + fin * ES;
-                const uint32_t tile_prev = (SKEW && y > y_start) ? ring_a + prev_stage * L.stage_bytes + lane * LANE_STRIDE : tile_addr;
+                constexpr int LSTR = VL ? R * ES : LANE_STRIDE;  // where a lane's first token starts inside a tile
+                const uint32_t tile_addr = ring_a + stage * L.stage_bytes + lane * LSTR + fin * ES;
+                const uint32_t tile_prev = (SKEW && y > y_start) ? ring_a + prev_stage * L.stage_bytes + lane * LSTR : tile_addr;
                 const int yl = y - lag;
                 if (y < diag_end)
-                    forward_unit<R, TF, UNIT, SKEW, true, VT>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
+                    forward_unit<R, TF, UNIT, SKEW, true, VT, VL>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
                                                           xl0 - yl, bits_row, TXS, y_start, (unsigned)span);
                 else
-                    forward_unit<R, TF, UNIT, SKEW, false, VT>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
+                    forward_unit<R, TF, UNIT, SKEW, false, VT, VL>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
                                                            0, bits_row, TXS, y_start, (unsigned)span);
                 seen_in = next_in;
                 seen_cons = next_cons;
@@ -936,7 +943,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 if (lane < nvalid) {
                     const int tok = tokb - __popc(moves & ((1u << (31 - lane)) - 1u));   // steps at frames above ours (mask is bit-reversed)
                     const int yy = yb + lane;
-                    if (p.paths != nullptr) store_one(p.paths, item * item_elems + (int64_t)tok * Ty + yy, p.esize, p.one);
+                    if (p.paths != nullptr) store_one(p.paths, item * item_elems + (VL ? (int64_t)yy * p.Tx + tok : (int64_t)tok * Ty + yy), p.esize, p.one);
                     if (p.frame_tok != nullptr) p.frame_tok[(int64_t)item * Ty + yy] = tok;
                     if (p.durations != nullptr) atomicAdd(&durS[tok], 1);
                 }

@@ -110,13 +110,37 @@ def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, return_durations: b
 
 def maximum_path_vits(neg_cent: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """VITS-layout entry: ``neg_cent`` and ``mask`` are ``[b, t_mel, t_text]`` as in VITS'
-    ``monotonic_align.maximum_path`` (its core indexes ``value[y, x]``), the result has the same layout.
+    ``monotonic_align.maximum_path`` (its core indexes ``value[y, x]``); the result has the same layout, dtype rule and
+    device rule as ``maximum_path``.
 
-    The search itself is layout-agnostic; this entry hands the kernel the ``[b, t_text, t_mel]`` view: the mask is read
-    through its strides (no copy), the scores are made contiguous by one device transpose (the kernels stream along the
-    mel axis), and the returned path is the transposed view of the kernel's output (no copy)."""
+    The search is layout-agnostic.  fp32 scores in the latency regime (batch <= #SMs, t_text <= 512, t_text % 4 == 0) are read
+    in place by kernels whose TMA boxes are taken from the ``[b*t_mel, t_text]`` view, and the path is written directly in
+    that layout; every other case hands ``maximum_path`` the transposed view (one device transpose of the scores; mask
+    and result are strided views, no copy)."""
     if neg_cent.dim() != 3 or mask.shape != neg_cent.shape:
         raise ValueError("expected neg_cent and mask of shape [b, t_mel, t_text]")
+    if mask.device != neg_cent.device:
+        raise ValueError("mask and neg_cent must be on the same device")
+    dtype = torch.result_type(neg_cent, mask)
+    if dtype not in _ONE or mask.dtype not in _MASK_DTYPE:
+        raise TypeError("unsupported dtype combination %s / %s" % (neg_cent.dtype, mask.dtype))
+    b, ty, tx = neg_cent.shape
+    if neg_cent.is_cuda and neg_cent.dtype == torch.float32 and b and tx and ty:
+        v = neg_cent.detach().contiguous()
+        esize, one = _ONE[dtype]
+        with torch.cuda.device(v.device):
+            path = torch.empty((b, ty, tx), dtype=dtype, device=v.device)
+            stream = torch.cuda.current_stream(v.device).cuda_stream
+            ws = _workspace(v.device, stream, b, tx, ty)
+            m = mask.detach()
+            sb, sy, sx = m.stride()                              # mask is [b, t_mel, t_text]; the kernel wants (b, text, mel) strides
+            rc = _lib.lib.alb200_mas_device_ex(v.data_ptr(), _lib.F32 | _lib.LAYOUT_VITS, None, None, m.data_ptr(), _MASK_DTYPE[m.dtype],
+                                               sb, sx, sy, None, path.data_ptr(), esize, one, 1, None, None, None,
+                                               b, tx, ty, -1e9, ws.data_ptr(), ws.numel(), stream)
+        if rc == 0:
+            return path
+        if rc != _lib.E_UNSUPPORTED:
+            _lib.check(rc)
     return maximum_path(neg_cent.transpose(1, 2), mask.transpose(1, 2)).transpose(1, 2)
 
 

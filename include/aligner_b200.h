@@ -31,6 +31,9 @@ extern "C" {
 #define ALB200_F32  0
 #define ALB200_F16  1
 #define ALB200_BF16 2
+/* OR into value_dtype of alb200_mas_device_ex: scores AND path are stored [b, t_mel, t_text] (the VITS convention,
+ * its core indexes value[y, x]) instead of the reference's [b, t_text, t_mel]; tx / ty keep their meaning. */
+#define ALB200_LAYOUT_VITS 0x100
 #define ALB200_F64  3
 #define ALB200_U8   4   /* also torch.bool */
 #define ALB200_I8   5
@@ -94,6 +97,9 @@ int alb200_mas_device_ordered(const float *values, const int32_t *t_xs, const in
  *                pick (<= 4 rows per lane in the latency regime, the throughput regime); otherwise the call returns
  *                ALB200_E_UNSUPPORTED and the caller promotes to fp32 on the device first (the Python layer does).
  *   lengths      either (t_xs, t_ys) or mask (+ strides in elements), as in alb200_mas_device / _masked.
+ *   layout       value_dtype | ALB200_LAYOUT_VITS: scores and path are [b, t_mel, t_text] (mask strides are still given
+ *                as (b, text, mel)).  Native for fp32 in the latency regime with <= 4 rows per lane and t_x % 4 == 0;
+ *                otherwise ALB200_E_UNSUPPORTED (the Python layer then transposes on the device).
  *   order        optional, as in alb200_mas_device_ordered. */
 int alb200_mas_device_ex(const void *values, int value_dtype, const int32_t *t_xs, const int32_t *t_ys,
                          const void *mask, int mask_dtype, int64_t mask_stride_b, int64_t mask_stride_x, int64_t mask_stride_y,

@@ -84,17 +84,27 @@ def test_differential_small(ma, monkeypatch, force, kind):
         check_against_oracle(ma, values, t_x, t_y)
 
 
-def test_vits_layout_entry(ma):
+@pytest.mark.parametrize("shape,native", [((6, 72, 190), True), ((3, 200, 403), True), ((2, 500, 640), True), ((9, 24, 33), True),
+                                          ((6, 70, 190), False),        # t_text % 4 != 0: transposed on the device
+                                          ((300, 72, 100), False),      # throughput regime
+                                          ((2, 600, 700), False)])      # cluster shapes
+def test_vits_layout_entry(ma, shape, native):
     """[b, t_mel, t_text] in and out, as VITS calls it; same search (its core indexes value[y, x])."""
-    rng = np.random.default_rng(21)
-    b, tx, ty = 6, 70, 190
+    rng = np.random.default_rng(abs(hash(shape)) % (2 ** 31))
+    b, tx, ty = shape
     values = make_values(rng, "gauss", (b, tx, ty))
     t_x, t_y = random_lengths(rng, b, tx, ty)
     want = oracle_paths(values, t_x, t_y)
     v = torch.from_numpy(np.ascontiguousarray(values.transpose(0, 2, 1))).cuda()                    # [b, t_mel, t_text]
     m = torch.from_numpy(np.ascontiguousarray(prefix_mask_np(t_x, t_y, tx, ty).transpose(0, 2, 1))).cuda()
+    n0 = _lib.launch_count()
     got = ma.maximum_path_vits(v, m)
     assert got.shape == v.shape and got.dtype == v.dtype
+    assert np.array_equal(got.cpu().numpy(), want.transpose(0, 2, 1).astype(np.float32))
+    assert got.is_contiguous() == native                  # the native kernels write the [b, t_mel, t_text] result directly
+    assert _lib.launch_count() == n0 + 1
+    # bool mask, int result
+    got = ma.maximum_path_vits(v, m.bool())
     assert np.array_equal(got.cpu().numpy(), want.transpose(0, 2, 1).astype(np.float32))
 
 

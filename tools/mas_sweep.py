@@ -36,7 +36,8 @@ def bench(b, tx, ty, force, ragged=False, reps=30, dense=True):
     nsets = int(min(max(2, np.ceil(400e6 / per_set) + 1), 8))
     g = torch.Generator(device=dev).manual_seed(1)
     vd = {"f32": (torch.float32, _lib.F32, 4), "f16": (torch.float16, _lib.F16, 2), "bf16": (torch.bfloat16, _lib.BF16, 2)}[os.environ.get("VDTYPE", "f32")]
-    vals = [torch.randn(b, tx, ty, generator=g, device=dev).to(vd[0]) for _ in range(nsets)]
+    vits = os.environ.get("VITS", "0") == "1"            # scores and path stored [b, t_mel, t_text]
+    vals = [torch.randn(*((b, ty, tx) if vits else (b, tx, ty)), generator=g, device=dev).to(vd[0]) for _ in range(nsets)]
     outs = [torch.empty(b, tx, ty, device=dev) for _ in range(nsets)]
     xl, yl = torch.from_numpy(t_x).to(dev), torch.from_numpy(t_y).to(dev)
     ws = ma._workspace(dev, torch.cuda.current_stream().cuda_stream, b, tx, ty)
@@ -47,7 +48,7 @@ def bench(b, tx, ty, force, ragged=False, reps=30, dense=True):
         return {"error": str(e)}
 
     def launch(i):
-        _lib.check(_lib.lib.alb200_mas_device_ex(vals[i % nsets].data_ptr(), vd[1], xl.data_ptr(), yl.data_ptr(), None, 0, 0, 0, 0, None,
+        _lib.check(_lib.lib.alb200_mas_device_ex(vals[i % nsets].data_ptr(), vd[1] | (_lib.LAYOUT_VITS if vits else 0), xl.data_ptr(), yl.data_ptr(), None, 0, 0, 0, 0, None,
                                                  outs[i % nsets].data_ptr() if dense else None, 4, 0x3F800000, 1, None, None, None,
                                                  b, tx, ty, -1e9, ws.data_ptr(), ws.numel(), stream))
     for i in range(3):
