@@ -270,8 +270,13 @@ static int values_tensor_map(const void* values, int vt, int vl, int b, int tx, 
     cuuint64_t strides[1] = { (cuuint64_t)(vl ? tx : ty) * (vt ? 2 : 4) };
     cuuint32_t box[2] = { (cuuint32_t)(vl ? box_rows : box_frames), (cuuint32_t)(vl ? box_frames : box_rows) }, es[2] = { 1, 1 };
     const CUtensorMapDataType dt = vt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (vt == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char* e = getenv("ALB200_TMAP_PROMO")) {      // tuning aid: 0 none, 1 64 B, 2 128 B, 3 256 B
+        const int v = atoi(e);
+        promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }
     CUresult r = enc(out, dt, 2, const_cast<void*>(values), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ALB200_E_CUDA, "cuTensorMapEncodeTiled failed with %s%lld", "", (long long)r);
     keys[next] = k; maps[next] = *out;
     next = (next + 1) % 16; if (used < 16) ++used;
