@@ -54,7 +54,7 @@ static int device_info(DevInfo* out)
 }
 
 // ------------------------------------------------------------------ kernel table
-typedef void (*KernelFn)(const MasParams, const CUtensorMap);
+typedef void (*KernelFn)(const MasParams, const CUtensorMap, const CUtensorMap);
 struct KEntry { int R, TF, skew, nwmax, minb; KernelFn fn; int vt; };     // vt: score element type (0 fp32, 1 fp16, 2 bf16)
 // lock-step form: a 255-register instance for the latency regime and a 128-register one for two CTAs per SM;
 // skewed form: latency regime only.
@@ -329,9 +329,21 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
     p.aligned = aligned ? 1 : 0;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
+    CUtensorMap tmap_tail;
+    memset(&tmap_tail, 0, sizeof(tmap_tail));
+    p.tail_rows = 32 * c.R;
     if (c.skew) {
         rc = values_tensor_map(values, vt, vl, b, tx, ty, 32 * c.R, c.TF, &tmap);
         if (rc) return rc;
+        // rows the last compute warp of the padded text axis really has, rounded up to 8 (TMA box rows are not free)
+        const int last = tx - (c.nc * c.NW - 1) * 32 * c.R;
+        if (!vl && last > 0 && last < 32 * c.R && !getenv("ALB200_NO_TAIL_BOX")) {
+            p.tail_rows = (last + 7) & ~7;
+            if (p.tail_rows < 32 * c.R) {
+                rc = values_tensor_map(values, vt, vl, b, tx, ty, p.tail_rows, c.TF, &tmap_tail);
+                if (rc) return rc;
+            }
+        }
     }
     p.neg = neg;
     static long long* d_dbg = nullptr;
@@ -343,7 +355,7 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
         ALB_CUDA(cudaMemset(d_dbg, 0, dbg_n * 8));
         p.dbg = d_dbg;
     }
-    void* args[] = { &p, &tmap };
+    void* args[] = { &p, &tmap, &tmap_tail };
     if (c.nc > 1) {
         cudaLaunchConfig_t lc;
         memset(&lc, 0, sizeof(lc));

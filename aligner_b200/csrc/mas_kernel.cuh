@@ -90,6 +90,7 @@ struct MasParams {
     int nblk;                   // ceil(Ty/32)
     int aligned;                // values base and Ty allow 16-byte copies
     int nc;                     // CTAs per utterance (thread-block cluster; 1 = one CTA per utterance)
+    int tail_rows;              // skewed form: token rows in the box of the LAST compute warp of the utterance (second tensor map)
     float neg;
     uint32_t off_full, off_empty, off_xbar, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, off_bt, stage_bytes;   // make_layout(), done on the host
 };
@@ -564,7 +565,7 @@ __device__ __forceinline__ void backtrack_walk(const uint32_t* bits, int TXS, in
 // NWMAX bounds the compute warps of an instance (4 -> 256 threads, 8 -> 512 threads).  MINB = 2 holds an instance to 128
 // registers so two CTAs share an SM (throughput regime); MINB = 1 lets an utterance that owns its SM use up to 255.
 template <int R, int TF, bool SKEW, int NWMAX, int MINB, bool CL = false, int VT = 0, bool VL = false>
-__global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasParams p, const __grid_constant__ CUtensorMap tmap)
+__global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail)
 {
     constexpr int RW = 32 * R;
     // hand-off granularity between warps: a whole 32-frame tile when an utterance owns its SM (fewer flag/barrier round trips per
@@ -745,10 +746,13 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                     if (SKEW) {
                         // one 2-D box load per tile: all 32*R rows of this warp x TF frames (the host only picks this form for
                         // 16-byte aligned inputs); rows past t_x and frames past T_mel are fetched or zero-filled, never used
+                        // The last compute warp of the (padded) text axis is usually only partly filled: it fetches a shorter box
+                        // through a second tensor map -- every box row costs TMA engine time (profiles/r01_notes.md).
                         if (lane == 0) {
-                            mbar_expect_tx(full0 + 8 * stage, RW * TF * ES);
+                            const bool tail = !VL && (gw == NC * NW - 1) && p.tail_rows < RW;
+                            mbar_expect_tx(full0 + 8 * stage, (tail ? p.tail_rows : RW) * TF * ES);
                             if (VL) tma_load_2d(st, &tmap, x0, item * Ty + t * TF, full0 + 8 * stage);      // box = RW tokens x TF frames of [b*t_mel, t_text]
-                            else tma_load_2d(st, &tmap, t * TF, item * p.Tx + x0, full0 + 8 * stage);
+                            else tma_load_2d(st, tail ? &tmap_tail : &tmap, t * TF, item * p.Tx + x0, full0 + 8 * stage);
                         }
                     } else if (p.aligned) {
                         // Loader lane = (16-byte chunk ck of a row, row group q0); it walks the owner lanes li = q0, q0+RPI, ...
