@@ -22,24 +22,25 @@ extern "C" {
 
 #define ALB200_OK              0
 #define ALB200_E_INVALID      -1   /* bad argument (null pointer, non-positive size, unknown dtype) */
-#define ALB200_E_UNSUPPORTED  -2   /* shape outside what the kernels cover (t_x > 8192) */
+#define ALB200_E_UNSUPPORTED  -2   /* shape outside what the kernels cover (t_x too long for the shared-memory ring), or no native
+                                      kernel for the requested score dtype / layout at this shape (alb200_mas_device_ex) */
 #define ALB200_E_CUDA         -3   /* a CUDA runtime call failed; see alb200_last_error() */
 #define ALB200_E_LENGTHS      -4   /* an item has t_x > t_y, or lengths outside the tensor */
 #define ALB200_E_NO_DEVICE    -5   /* no sm_100 device: this library has no fallback */
 
-/* element types of a mask tensor (alb200_mas_device_masked) */
+/* element types: of a mask tensor (alb200_mas_device_masked, all of them) and of the scores (alb200_mas_device_ex: F32, F16, BF16) */
 #define ALB200_F32  0
 #define ALB200_F16  1
 #define ALB200_BF16 2
-/* OR into value_dtype of alb200_mas_device_ex: scores AND path are stored [b, t_mel, t_text] (the VITS convention,
- * its core indexes value[y, x]) instead of the reference's [b, t_text, t_mel]; tx / ty keep their meaning. */
-#define ALB200_LAYOUT_VITS 0x100
 #define ALB200_F64  3
 #define ALB200_U8   4   /* also torch.bool */
 #define ALB200_I8   5
 #define ALB200_I16  6
 #define ALB200_I32  7
 #define ALB200_I64  8
+/* OR into value_dtype of alb200_mas_device_ex: scores AND path are stored [b, t_mel, t_text] (the VITS convention,
+ * its core indexes value[y, x]) instead of the reference's [b, t_text, t_mel]; tx / ty keep their meaning. */
+#define ALB200_LAYOUT_VITS 0x100
 
 const char *alb200_last_error(void);
 /* "aligner_b200 <version> sm_100a" */
