@@ -217,6 +217,13 @@ __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta,
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
 }
+// 16-byte store from registers into another CTA's shared memory whose bytes complete on an mbarrier over there (SASS STAS.128):
+// data and "it has arrived" travel together, no fence on either side.
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster, float4 v, uint32_t mbar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
+                 ::"r"(dst_cluster), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)), "r"(mbar_cluster)
+                 : "memory");
+}
 __device__ __forceinline__ void st_cluster_flag(uint32_t a, int v) {
     asm volatile("st.relaxed.cluster.shared::cluster.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
@@ -815,8 +822,10 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             const uint32_t in_tail = tail_a + 4 * (w > 0 ? w - 1 : 0);
             const uint32_t out_head = remote_out ? xout_head_a : head_a + 4 * (has_consumer ? w + 1 : w);
             // Cluster hand-off: the producer (last warp of CTA c) writes its local ring as usual and, once per unit, lane 31
-            // ships the unit's 32 boundary values to ring 0 of CTA c+1 with ONE shared->remote-shared bulk copy whose bytes
-            // complete on an mbarrier over there; the consumer arms and waits on that mbarrier.  No fences on either side.
+            // reads its own 32 boundary values back and sends them to ring 0 of CTA c+1 with eight st.async (STAS.128) whose
+            // bytes complete on an mbarrier over there; the consumer arms (expect_tx 128) and waits on that mbarrier.  No
+            // fences on either side.  (Inside the unit body the stores turn into one branch per group, ptxas will not
+            // predicate STAS; a shared->remote bulk copy needs fence.proxy.async, ~400 cycles -- profiles/r01_notes.md.)
             const uint32_t r_ring = remote_out ? mapa_u32(bnd_a, (uint32_t)crank + 1) : 0u;         // next CTA's ring 0
             const uint32_t r_xbar = remote_out ? mapa_u32(xbar_a, (uint32_t)crank + 1) : 0u;
             const uint32_t r_head = remote_in ? mapa_u32(xout_head_a, (uint32_t)crank - 1) : 0u;    // where the previous CTA polls our progress
@@ -896,8 +905,9 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                     if (remote_out && lane31) {                  // ship this unit's 32 boundary values (written by this very lane)
                         const uint32_t off = (uint32_t)(y & (kRing - 1)) << 2;
                         const int k = (y - y_start) >> 5;
-                        fence_proxy_async_smem();                // generic-proxy writes above -> visible to the bulk copy
-                        bulk_s2c(r_ring + off, bout_addr + off, 128, r_xbar + 8 * (k & 3));   // the local slots are rewritten 4 units from now
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)              // same thread wrote these slots: program order, no fence
+                            st_async_v4(r_ring + off + 16 * g, lds128(bout_addr + off + 16 * g), r_xbar + 8 * (k & 3));
                     }
                     if (remote_in && lane0) st_cluster_flag(r_head, y + UNIT);
                 }
