@@ -159,6 +159,21 @@ def test_processing_order_does_not_change_results(ma):
         assert np.array_equal(out["durations"].cpu().numpy(), want.sum(-1))
 
 
+@pytest.mark.parametrize("shape", [(1, 2048, 2304),      # cluster of 8 CTAs
+                                   (1, 3000, 3200),      # 16 rows per lane, lock-step
+                                   (2, 1, 5000), (1, 4, 20000),      # one token / very long mel axis
+                                   (3, 513, 516),        # cluster of 3, almost square band
+                                   (150, 513, 600),      # more clusters than fit: single-CTA throughput form
+                                   (5, 33, 33), (2, 2047, 2050)])    # square; unaligned rows with 8 compute warps
+def test_extreme_shapes(ma, shape):
+    rng = np.random.default_rng(abs(hash(shape)) % (2 ** 31))
+    b, tx, ty = shape
+    values = make_values(rng, "gauss", shape)
+    t_x, t_y = random_lengths(rng, b, tx, ty)
+    t_x[0], t_y[0] = tx, ty
+    check_against_oracle(ma, values, t_x, t_y)
+
+
 # ------------------------------------------------------------------ cluster mode: one utterance split over the CTAs of a cluster
 @pytest.mark.parametrize("force,txmax", [("1,32,3,0,1,2", 256), ("2,32,3,0,1,2", 512), ("2,32,2,0,1,4", 1024), ("1,32,4,0,1,8", 1024),
                                          ("3,32,2,0,1,3", 1152)])
