@@ -78,6 +78,15 @@ def main():
         "c4": (8, 1000, 6000, False, [None, "8,16,2,0,0,1", "2,32,3,0,1,4", "2,32,2,0,1,4", "3,32,2,0,1,3", "4,32,2,0,1,2", "4,32,3,0,1,2", "1,32,4,0,1,8"]),
         "c4b": (16, 768, 3072, False, [None, "6,16,4,0,0,1", "2,32,3,0,1,3", "3,32,2,0,1,2", "4,32,2,0,1,2"]),
         "c4c": (32, 640, 3200, False, [None, "6,16,4,0,0,1", "2,32,3,0,1,3", "4,32,2,0,1,2"]),
+        "m1": (300, 200, 1000, False, [None, "0,0,0,-1,1"]),
+        "m2": (500, 200, 1000, False, [None, "0,0,0,-1,1"]),
+        "m3": (300, 100, 800, False, [None, "0,0,0,-1,1"]),
+        "m4": (600, 400, 2000, True, [None, "0,0,0,-1,1"]),
+        "m5": (200, 300, 1500, True, [None, "0,0,0,-1,1"]),
+        "m6": (700, 200, 1000, True, [None, "0,0,0,-1,1"]),
+        "c5s": (256, 400, 2000, True, [None, "4,32,2,0,1", "4,32,3,0,1", "4,32,2,0,0"]),
+        "c5m": (512, 400, 2000, True, [None, "4,32,2,0,1", "4,32,3,0,1"]),
+        "c5l": (1024, 400, 2000, True, [None, "4,32,3,0,1"]),
         "c5a": (2048, 400, 2000, True, [None, "4,16,3,0,0", "8,16,2,0,0", "8,16,3,0,0", "8,8,3,0,0", "8,8,4,0,0", "6,16,2,0,0", "8,32,2,0,0"]),
         "c5b": (4096, 200, 1000, False, [None, "4,16,2,0,0", "4,16,3,0,0", "4,32,2,0,0", "4,32,2,1,0", "6,16,2,0,0", "8,16,2,0,0", "3,16,2,0,0"]),
         "c5c": (4096, 100, 800, False, [None, "2,16,2,0,0", "2,16,3,0,0", "2,32,2,0,0", "4,16,2,0,0", "4,32,2,1,0", "1,32,2,1,0"]),
