@@ -84,6 +84,9 @@ def main():
         "m4": (600, 400, 2000, True, [None, "0,0,0,-1,1"]),
         "m5": (200, 300, 1500, True, [None, "0,0,0,-1,1"]),
         "m6": (700, 200, 1000, True, [None, "0,0,0,-1,1"]),
+        "x1": (900, 200, 1000, True, [None]), "x2": (1200, 200, 1000, True, [None]), "x3": (1600, 200, 1000, True, [None]), "x4": (2400, 200, 1000, True, [None]),
+        "x5": (900, 400, 2000, True, [None]), "x6": (1200, 400, 2000, True, [None]),
+        "x7": (900, 100, 800, False, [None]), "x8": (1600, 100, 800, False, [None]), "x9": (3000, 100, 800, False, [None]),
         "c5s": (256, 400, 2000, True, [None, "4,32,2,0,1", "4,32,3,0,1", "4,32,2,0,0"]),
         "c5m": (512, 400, 2000, True, [None, "4,32,2,0,1", "4,32,3,0,1"]),
         "c5l": (1024, 400, 2000, True, [None, "4,32,3,0,1"]),
