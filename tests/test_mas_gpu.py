@@ -86,8 +86,8 @@ def test_differential_small(ma, monkeypatch, force, kind):
 
 @pytest.mark.parametrize("shape,native", [((6, 72, 190), True), ((3, 200, 403), True), ((2, 500, 640), True), ((9, 24, 33), True),
                                           ((6, 70, 190), False),        # t_text % 4 != 0: transposed on the device
-                                          ((300, 72, 100), True),       # several SMs' worth: still the skewed form, persistent grid
-                                          ((600, 72, 100), False),      # throughput regime
+                                          ((300, 72, 640), True),       # several SMs' worth: still the skewed form, persistent grid
+                                          ((300, 72, 100), False),      # throughput regime
                                           ((2, 600, 700), False)])      # cluster shapes
 def test_vits_layout_entry(ma, shape, native):
     """[b, t_mel, t_text] in and out, as VITS calls it; same search (its core indexes value[y, x])."""
@@ -163,12 +163,13 @@ def test_processing_order_does_not_change_results(ma):
 def test_midsize_batch_runs_the_skewed_form_persistently(ma):
     """Several SMs' worth of utterances with t_x <= 512: one CTA per SM, skewed/TMA form, work cursor across many items."""
     rng = np.random.default_rng(91)
-    for (b, tx, ty) in [(500, 150, 400), (420, 100, 240), (300, 400, 640)]:
+    for (b, tx, ty) in [(500, 150, 640), (420, 100, 600), (300, 400, 640)]:
         assert "form=skewed" in _lib.describe(b, tx, ty)
         values = make_values(rng, "gauss", (b, tx, ty))
         t_x, t_y = random_lengths(rng, b, tx, ty)
         check_against_oracle(ma, values, t_x, t_y)
-    assert "form=lockstep" in _lib.describe(4096, 200, 1000)            # a full machine's worth: occupancy-driven form
+    assert "form=lockstep" in _lib.describe(4096, 100, 800)             # a full machine's worth of short utterances: occupancy-driven form
+    assert "form=lockstep" in _lib.describe(500, 150, 400)              # short mel axis: the pipeline fill would not be amortised
 
 
 @pytest.mark.parametrize("shape", [(1, 2048, 2304),      # cluster of 8 CTAs

@@ -87,6 +87,10 @@ def main():
         "x1": (900, 200, 1000, True, [None]), "x2": (1200, 200, 1000, True, [None]), "x3": (1600, 200, 1000, True, [None]), "x4": (2400, 200, 1000, True, [None]),
         "x5": (900, 400, 2000, True, [None]), "x6": (1200, 400, 2000, True, [None]),
         "x7": (900, 100, 800, False, [None]), "x8": (1600, 100, 800, False, [None]), "x9": (3000, 100, 800, False, [None]),
+        "y1": (4096, 100, 800, False, [None, "2,32,2,1,1", "2,32,3,1,1", "2,32,4,1,1", "2,32,2,0,1", "1,32,3,1,1", "1,32,4,1,1"]),
+        "y2": (2048, 400, 2000, True, [None, "4,32,3,0,1", "4,32,2,0,1", "3,32,3,0,1"]),
+        "z1": (4096, 200, 300, False, [None]), "z2": (4096, 160, 500, True, [None]), "z3": (2048, 256, 2000, True, [None]), "z4": (3000, 130, 400, True, [None]),
+        "q1": (500, 160, 500, True, [None]), "q2": (400, 100, 300, False, [None]), "q3": (600, 300, 500, True, [None]), "q4": (1000, 200, 640, True, [None]),
         "c5s": (256, 400, 2000, True, [None, "4,32,2,0,1", "4,32,3,0,1", "4,32,2,0,0"]),
         "c5m": (512, 400, 2000, True, [None, "4,32,2,0,1", "4,32,3,0,1"]),
         "c5l": (1024, 400, 2000, True, [None, "4,32,3,0,1"]),
