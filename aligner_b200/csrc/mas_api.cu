@@ -94,13 +94,15 @@ static const KEntry g_kernels[] = {
 // b <= #SM; measured (profiles/r01_notes.md, item 21) it also beats the occupancy-driven throughput configuration for
 // several SMs' worth of utterances as long as the skewed form applies (t_x <= 512, 16-byte aligned rows) -- the more
 // compute warps one utterance keeps busy and the longer its mel axis, the longer.  ALB200_LATENCY_MAX_B overrides (tuning aid).
-static bool is_latency(const DevInfo& di, int b, int tx, int ty, bool aligned)
+static bool is_latency(const DevInfo& di, int b, int tx, int ty, bool aligned, int vt)
 {
     if (const char* e = getenv("ALB200_LATENCY_MAX_B")) return b <= atoi(e);
     if (b <= di.sms) return true;
     // one CTA per SM cannot hide an utterance's pipeline fill (~63 frames per compute warp) and backtrack behind other
     // utterances, so the mel axis has to be long enough to amortise them
-    if (!aligned || tx > 512 || ty < 600) return false;
+    // (half-precision scores: the lock-step form is the bandwidth-bound one and profits from the halved read -- 4096x200x1000
+    //  bf16 1.04 ms lock-step vs 1.18 ms skewed -- so beyond #SM utterances they stay there)
+    if (!aligned || tx > 512 || ty < 600 || vt != 0) return false;
     if (tx <= 128) return b <= 3 * di.sms;                       // two compute warps per SM only
     if (tx <= 256) return ty >= 1000 || b <= 12 * di.sms;        // 4096x200x1000: 81.7 % of HBM peak vs 76.7 %
     return b <= 5 * di.sms;
@@ -127,7 +129,7 @@ struct Config {
 //                    compute warps per SM hide each other's latency and one item's backtrack overlaps others' streaming.
 static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, int vt, int vl, Config* c)
 {
-    const bool latency = is_latency(di, b, tx, ty, aligned);
+    const bool latency = is_latency(di, b, tx, ty, aligned, vt);
     int R, NW;
     if (tx <= 32) { R = 1; NW = 1; }
     else if (latency) {
@@ -236,7 +238,7 @@ static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur
     static thread_local int used = 0, next = 0;
     CfgKey k;
     memset(&k, 0, sizeof(k));
-    k.dev = di.dev; k.latency = is_latency(di, b, tx, ty, aligned); k.tx = tx; k.ty = ty; k.dur = want_dur; k.aligned = aligned; k.vt = vt; k.vl = vl;
+    k.dev = di.dev; k.latency = is_latency(di, b, tx, ty, aligned, vt); k.tx = tx; k.ty = ty; k.dur = want_dur; k.aligned = aligned; k.vt = vt; k.vl = vl;
     k.bclass = (k.latency && tx > 512) ? b : 0;                 // the cluster decision depends on how many clusters fit
     if (const char* f = getenv("ALB200_FORCE")) strncpy(k.env, f, sizeof(k.env) - 1);
     int hit = -1;
