@@ -21,7 +21,7 @@ LAYOUT_VITS = 0x100   # OR into the value dtype of alb200_mas_device_ex: scores 
 
 # every symbol include/aligner_b200.h declares (tests check the export list against the header)
 SYMBOLS = (
-    "alb200_last_error", "alb200_version", "alb200_mas_device", "alb200_mas_device_ordered", "alb200_mas_device_ex", "alb200_mas_device_masked",
+    "alb200_last_error", "alb200_version", "alb200_set_option", "alb200_mas_device", "alb200_mas_device_ex", "alb200_mas_device_masked",
     "alb200_mas_workspace_bytes", "alb200_mas_status", "alb200_mas_describe", "alb200_maximum_path_c",
     "alb200_last_transfer_bytes", "alb200_launch_count",
     "alb200_neg_cent_gaussian", "alb200_neg_cent_ota",
@@ -49,9 +49,9 @@ def _load() -> ctypes.CDLL:
     lib.alb200_last_transfer_bytes.restype = None
     lib.alb200_mas_device.argtypes = [vp, vp, vp, vp, i32, u64, i32, vp, vp, i32, i32, i32, f32, vp, sz, vp]
     lib.alb200_mas_device.restype = i32
-    lib.alb200_mas_device_ordered.argtypes = [vp, vp, vp, vp, vp, i32, u64, i32, vp, vp, i32, i32, i32, f32, vp, sz, vp]
-    lib.alb200_mas_device_ordered.restype = i32
-    lib.alb200_mas_device_ex.argtypes = [vp, i32, vp, vp, vp, i32, i64, i64, i64, vp, vp, i32, u64, i32, vp, vp, vp, i32, i32, i32, f32, vp, sz, vp]
+    lib.alb200_set_option.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    lib.alb200_set_option.restype = i32
+    lib.alb200_mas_device_ex.argtypes = [vp, i32, vp, vp, vp, i32, i64, i64, i64, vp, i32, u64, i32, vp, vp, vp, i32, i32, i32, f32, vp, sz, vp]
     lib.alb200_mas_device_ex.restype = i32
     lib.alb200_mas_device_masked.argtypes = [vp, vp, i32, i64, i64, i64, vp, i32, u64, i32, vp, vp, vp,
                                              i32, i32, i32, f32, vp, sz, vp]
@@ -77,6 +77,11 @@ lib = _load()
 def check(rc: int) -> None:
     if rc != OK:
         raise AlignerB200Error(rc, lib.alb200_last_error().decode("utf-8", "replace"))
+
+
+def set_option(name: str, value=None) -> None:
+    """Tuning / test options (include/aligner_b200.h: alb200_set_option); value None restores the default."""
+    check(lib.alb200_set_option(name.encode(), None if value is None else str(value).encode()))
 
 
 def describe(b: int, tx: int, ty: int, want_durations: bool = False) -> str:

@@ -5,14 +5,51 @@
 // There is no CPU fallback in this file: without an sm_100 device every entry
 // point returns ALB200_E_NO_DEVICE.
 #include "mas_kernel.cuh"
+#include "alb_opts.h"
 #include "../../include/aligner_b200.h"
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <mutex>
 
 namespace alb {
+
+// ------------------------------------------------------------------ options (environment read once, alb200_set_option afterwards)
+static Opts g_opts;
+static std::once_flag g_opts_once;
+static std::mutex g_opts_mu;
+static int set_opt_locked(const char* name, const char* value)
+{
+    const bool unset = (value == nullptr || value[0] == '\0');
+    if (!strcmp(name, "force")) { memset(g_opts.force, 0, sizeof(g_opts.force)); if (!unset) strncpy(g_opts.force, value, sizeof(g_opts.force) - 1); }
+    else if (!strcmp(name, "latency_max_b")) g_opts.latency_max_b = unset ? -1 : atoi(value);
+    else if (!strcmp(name, "tmap_promo")) g_opts.tmap_promo = unset ? -1 : atoi(value);
+    else if (!strcmp(name, "no_tail_box")) g_opts.no_tail_box = unset ? 0 : atoi(value) != 0;
+    else if (!strcmp(name, "force_unaligned")) g_opts.force_unaligned = unset ? 0 : atoi(value) != 0;
+    else if (!strcmp(name, "dbg")) g_opts.dbg = unset ? 0 : atoi(value) != 0;
+    else if (!strcmp(name, "nc_ffma")) g_opts.nc_ffma = unset ? 0 : atoi(value) != 0;
+    else if (!strcmp(name, "nc_v1")) g_opts.nc_v1 = unset ? 0 : atoi(value) != 0;
+    else return -1;
+    ++g_opts.gen;
+    return 0;
+}
+static void opts_from_env()
+{
+    memset(&g_opts, 0, sizeof(g_opts));
+    g_opts.latency_max_b = -1; g_opts.tmap_promo = -1;
+    static const char* const names[][2] = { {"ALB200_FORCE", "force"}, {"ALB200_LATENCY_MAX_B", "latency_max_b"}, {"ALB200_TMAP_PROMO", "tmap_promo"},
+        {"ALB200_NO_TAIL_BOX", "no_tail_box"}, {"ALB200_FORCE_UNALIGNED", "force_unaligned"}, {"ALB200_DBG", "dbg"}, {"ALB200_NC_FFMA", "nc_ffma"},
+        {"ALB200_NC_V1", "nc_v1"} };
+    for (auto& n : names)
+        if (const char* e = getenv(n[0])) set_opt_locked(n[1], e[0] ? e : "1");
+}
+const Opts& opts()
+{
+    std::call_once(g_opts_once, opts_from_env);
+    return g_opts;
+}
 
 thread_local char g_err[512] = "";          // also written by neg_cent.cu
 thread_local uint64_t g_launches = 0;
@@ -96,7 +133,7 @@ static const KEntry g_kernels[] = {
 // compute warps one utterance keeps busy and the longer its mel axis, the longer.  ALB200_LATENCY_MAX_B overrides (tuning aid).
 static bool is_latency(const DevInfo& di, int b, int tx, int ty, bool aligned, int vt)
 {
-    if (const char* e = getenv("ALB200_LATENCY_MAX_B")) return b <= atoi(e);
+    if (opts().latency_max_b >= 0) return b <= opts().latency_max_b;
     if (b <= di.sms) return true;
     // one CTA per SM cannot hide an utterance's pipeline fill (~63 frames per compute warp) and backtrack behind other
     // utterances, so the mel axis has to be long enough to amortise them
@@ -148,8 +185,8 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     }
     int f_tf = 0, f_ns = 0, f_bits = -1, f_skew = -1, f_nc = 0;
     int fr = 0;
-    if (const char* f = getenv("ALB200_FORCE"))    // "R,TF,NS,bits_smem,skew,cluster" -- tuning / tests only
-        sscanf(f, "%d,%d,%d,%d,%d,%d", &fr, &f_tf, &f_ns, &f_bits, &f_skew, &f_nc);
+    if (opts().force[0])                           // "R,TF,NS,bits_smem,skew,cluster" -- tuning / tests only
+        sscanf(opts().force, "%d,%d,%d,%d,%d,%d", &fr, &f_tf, &f_ns, &f_bits, &f_skew, &f_nc);
     // Cluster mode: an utterance whose text axis needs more than 4 rows per lane in one CTA (t_x > 512) loses the fast
     // skewed form; split its rows over the CTAs of a thread-block cluster instead (2 rows per lane, 4 compute warps per
     // CTA, boundary rows handed over through distributed shared memory).  Only when every cluster gets its own SMs.
@@ -229,28 +266,35 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     return 0;
 }
 
-// select_config_uncached costs a few driver calls; remember the answers (per thread, tiny table).
-struct CfgKey { int dev, latency, tx, ty, dur, aligned, bclass, vt, vl; char env[48]; };
+// select_config_uncached costs a few driver calls; remember the answers, failures included (per thread; 64 entries hold the
+// dur x aligned x dtype probes of alb200_mas_workspace_bytes for several shapes at once).
+struct CfgKey { int dev, latency, tx, ty, dur, aligned, bclass, vt, vl; unsigned gen; };
+constexpr int kCfgCache = 64;
 static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur, bool aligned, Config* c, int vt = 0, int vl = 0)
 {
-    static thread_local CfgKey keys[8];
-    static thread_local Config vals[8];
+    static thread_local CfgKey keys[kCfgCache];
+    static thread_local Config vals[kCfgCache];
+    static thread_local int rcs[kCfgCache];
+    static thread_local char errs[kCfgCache][160];
     static thread_local int used = 0, next = 0;
     CfgKey k;
     memset(&k, 0, sizeof(k));
     k.dev = di.dev; k.latency = is_latency(di, b, tx, ty, aligned, vt); k.tx = tx; k.ty = ty; k.dur = want_dur; k.aligned = aligned; k.vt = vt; k.vl = vl;
     k.bclass = (k.latency && tx > 512) ? b : 0;                 // the cluster decision depends on how many clusters fit
-    if (const char* f = getenv("ALB200_FORCE")) strncpy(k.env, f, sizeof(k.env) - 1);
+    k.gen = opts().gen;
     int hit = -1;
     for (int i = 0; i < used; ++i)
         if (memcmp(&keys[i], &k, sizeof(k)) == 0) { hit = i; break; }
     if (hit < 0) {
         Config fresh;
-        int rc = select_config_uncached(di, b, tx, ty, want_dur, aligned, vt, vl, &fresh);
-        if (rc) return rc;
-        hit = next; next = (next + 1) % 8; if (used < 8) ++used;
-        keys[hit] = k; vals[hit] = fresh;
+        memset(&fresh, 0, sizeof(fresh));
+        const int rc = select_config_uncached(di, b, tx, ty, want_dur, aligned, vt, vl, &fresh);
+        if (rc == ALB200_E_CUDA) return rc;                      // a failing driver call is not a property of the shape
+        hit = next; next = (next + 1) % kCfgCache; if (used < kCfgCache) ++used;
+        keys[hit] = k; vals[hit] = fresh; rcs[hit] = rc;
+        strncpy(errs[hit], g_err, sizeof(errs[hit]) - 1); errs[hit][sizeof(errs[hit]) - 1] = 0;
     }
+    if (rcs[hit]) { snprintf(g_err, sizeof(g_err), "%s", errs[hit]); return rcs[hit]; }
     *c = vals[hit];
     int64_t g = (int64_t)di.sms * c->occ;
     c->grid = c->nc > 1 ? b * c->nc : (int)(b < g ? b : g);
@@ -271,13 +315,13 @@ static int values_tensor_map(const void* values, int vt, int vl, int b, int tx, 
         if (!fn || q != cudaDriverEntryPointSuccess) return fail(ALB200_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver%s", "");
         enc = reinterpret_cast<TmapEncodeFn>(fn);
     }
-    struct Key { const void* v; int b, tx, ty, br, bf, vt, vl; };
+    struct Key { const void* v; int b, tx, ty, br, bf, vt, vl; unsigned gen; };
     static thread_local Key keys[16];
     static thread_local CUtensorMap maps[16];
     static thread_local int used = 0, next = 0;
-    const Key k = { values, b, tx, ty, box_rows, box_frames, vt, vl };
+    const Key k = { values, b, tx, ty, box_rows, box_frames, vt, vl, opts().gen };
     for (int i = 0; i < used; ++i)
-        if (keys[i].v == k.v && keys[i].b == b && keys[i].tx == tx && keys[i].ty == ty && keys[i].br == box_rows && keys[i].bf == box_frames && keys[i].vt == vt && keys[i].vl == vl) {
+        if (keys[i].v == k.v && keys[i].gen == k.gen && keys[i].b == b && keys[i].tx == tx && keys[i].ty == ty && keys[i].br == box_rows && keys[i].bf == box_frames && keys[i].vt == vt && keys[i].vl == vl) {
             *out = maps[i];
             return 0;
         }
@@ -289,8 +333,8 @@ static int values_tensor_map(const void* values, int vt, int vl, int b, int tx, 
     cuuint32_t box[2] = { (cuuint32_t)(vl ? box_rows : box_frames), (cuuint32_t)(vl ? box_frames : box_rows) }, es[2] = { 1, 1 };
     const CUtensorMapDataType dt = vt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (vt == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
     CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-    if (const char* e = getenv("ALB200_TMAP_PROMO")) {      // tuning aid: 0 none, 1 64 B, 2 128 B, 3 256 B
-        const int v = atoi(e);
+    if (opts().tmap_promo >= 0) {                           // tuning aid: 0 none, 1 64 B, 2 128 B, 3 256 B
+        const int v = opts().tmap_promo;
         promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     }
     CUresult r = enc(out, dt, 2, const_cast<void*>(values), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -309,7 +353,7 @@ static size_t ws_bytes_for(const Config& c)
 static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_ys, const void* mask, int mask_dtype,
                       int64_t msb, int64_t msx, int64_t msy, void* paths, int esize, uint64_t one, int zero_fill,
                       int32_t* frame_tok, int32_t* durations, int32_t* lens_out, int b, int tx, int ty, float neg,
-                      void* workspace, size_t workspace_bytes, cudaStream_t stream, const int32_t* order = nullptr, int vt = 0, int vl = 0)
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream, int vt = 0, int vl = 0)
 {
     if (!values || b < 0 || tx <= 0 || ty <= 0) return fail(ALB200_E_INVALID, "null values or non-positive shape%s", "");
     if (!mask && (!t_xs || !t_ys)) return fail(ALB200_E_INVALID, "need lengths or a mask%s", "");
@@ -324,14 +368,14 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
     Config c;
     if (vt < 0 || vt > 2) return fail(ALB200_E_INVALID, "unknown score dtype %s%lld", "", vt);
     bool aligned = (reinterpret_cast<uintptr_t>(values) & 15) == 0 && ((int64_t)(vl ? tx : ty) * (vt ? 2 : 4)) % 16 == 0;
-    if (getenv("ALB200_FORCE_UNALIGNED")) aligned = false;
+    if (opts().force_unaligned) aligned = false;
     rc = select_config(di, b, tx, ty, durations != nullptr, aligned, &c, vt, vl);
     if (rc) return rc;
     if (workspace_bytes < ws_bytes_for(c))
         return fail(ALB200_E_INVALID, "workspace too small: %s%lld < %lld bytes", "", (long long)workspace_bytes, (long long)ws_bytes_for(c));
     MasParams p;
     memset(&p, 0, sizeof(p));
-    p.values = values; p.paths = paths; p.t_xs = t_xs; p.t_ys = t_ys; p.order = order;
+    p.values = values; p.paths = paths; p.t_xs = t_xs; p.t_ys = t_ys;
     p.mask = mask; p.msb = msb; p.msx = msx; p.msy = msy; p.mask_dtype = mask_dtype;
     p.frame_tok = frame_tok; p.durations = durations; p.lens_out = lens_out;
     p.ws = reinterpret_cast<WsHeader*>(workspace);
@@ -355,7 +399,7 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
         if (rc) return rc;
         // rows the last compute warp of the padded text axis really has, rounded up to 8 (TMA box rows are not free)
         const int last = tx - (c.nc * c.NW - 1) * 32 * c.R;
-        if (!vl && last > 0 && last < 32 * c.R && !getenv("ALB200_NO_TAIL_BOX")) {
+        if (!vl && last > 0 && last < 32 * c.R && !opts().no_tail_box) {
             p.tail_rows = (last + 7) & ~7;
             if (p.tail_rows < 32 * c.R) {
                 rc = values_tensor_map(values, vt, vl, b, tx, ty, p.tail_rows, c.TF, &tmap_tail);
@@ -365,7 +409,7 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
     }
     p.neg = neg;
     static long long* d_dbg = nullptr;
-    const bool dbg = getenv("ALB200_DBG") != nullptr;
+    const bool dbg = kDbgBuild && opts().dbg;
     const size_t dbg_n = (size_t)c.grid * ((2 * kMaxWarps + 2) * 2 + kMaxWarps * 8);
     if (dbg) {   // developer aid: per-warp clock64 stamps of the first item of every CTA, printed to stderr
         if (d_dbg) cudaFree(d_dbg);
@@ -463,7 +507,15 @@ using namespace alb;
 extern "C" {
 
 const char* alb200_last_error(void) { return g_err; }
-const char* alb200_version(void) { return "aligner_b200 0.1.0 sm_100a"; }
+const char* alb200_version(void) { return "aligner_b200 0.2.0 sm_100a"; }
+int alb200_set_option(const char* name, const char* value)
+{
+    if (!name) return fail(ALB200_E_INVALID, "null option name%s", "");
+    opts();                                                   // the environment is read first, once
+    std::lock_guard<std::mutex> lk(g_opts_mu);
+    if (set_opt_locked(name, value)) return fail(ALB200_E_INVALID, "unknown option '%s'", name);
+    return 0;
+}
 uint64_t alb200_launch_count(void) { return g_launches; }
 void alb200_last_transfer_bytes(uint64_t* h2d, uint64_t* d2h) { if (h2d) *h2d = g_h2d; if (d2h) *d2h = g_d2h; }
 
@@ -475,16 +527,8 @@ int alb200_mas_device(const float* values, const int32_t* t_xs, const int32_t* t
                       durations, nullptr, b, tx, ty, max_neg_val, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int alb200_mas_device_ordered(const float* values, const int32_t* t_xs, const int32_t* t_ys, const int32_t* order, void* paths,
-                              int path_elem_size, uint64_t path_one, int zero_fill, int32_t* frame_tok, int32_t* durations, int b, int tx,
-                              int ty, float max_neg_val, void* workspace, size_t workspace_bytes, void* stream)
-{
-    return launch_mas(values, t_xs, t_ys, nullptr, 0, 0, 0, 0, paths, path_elem_size, path_one, zero_fill, frame_tok,
-                      durations, nullptr, b, tx, ty, max_neg_val, workspace, workspace_bytes, (cudaStream_t)stream, order);
-}
-
 int alb200_mas_device_ex(const void* values, int value_dtype, const int32_t* t_xs, const int32_t* t_ys, const void* mask, int mask_dtype,
-                         int64_t msb, int64_t msx, int64_t msy, const int32_t* order, void* paths, int path_elem_size, uint64_t path_one,
+                         int64_t msb, int64_t msx, int64_t msy, void* paths, int path_elem_size, uint64_t path_one,
                          int zero_fill, int32_t* frame_tok, int32_t* durations, int32_t* lens_out, int b, int tx, int ty, float max_neg_val,
                          void* workspace, size_t workspace_bytes, void* stream)
 {
@@ -498,7 +542,7 @@ int alb200_mas_device_ex(const void* values, int value_dtype, const int32_t* t_x
         default: return fail(ALB200_E_INVALID, "score dtype %s%lld is not fp32, fp16 or bf16", "", value_dtype);
     }
     return launch_mas(values, t_xs, t_ys, mask, mask_dtype, msb, msx, msy, paths, path_elem_size, path_one, zero_fill, frame_tok,
-                      durations, lens_out, b, tx, ty, max_neg_val, workspace, workspace_bytes, (cudaStream_t)stream, order, vt, vl);
+                      durations, lens_out, b, tx, ty, max_neg_val, workspace, workspace_bytes, (cudaStream_t)stream, vt, vl);
 }
 
 int alb200_mas_device_masked(const float* values, const void* mask, int mask_dtype, int64_t msb, int64_t msx, int64_t msy,
@@ -584,7 +628,9 @@ int alb200_maximum_path_c(int32_t* paths, const float* values, const int32_t* t_
     if ((rc = grow_dev(&X.d_lens, &X.cap_lens, (size_t)b * 8))) return rc;
     if ((rc = grow_host(&X.h_ftok, &X.cap_hftok, (size_t)b * ty * 4))) return rc;
     if ((rc = grow_host(&X.h_lens, &X.cap_hlens, (size_t)b * 8))) return rc;
-    const size_t wsz = alb200_mas_workspace_bytes(per, tx, ty);
+    // the last chunk can be smaller and pick another configuration (e.g. cluster mode with its bits in L2): size for both
+    const int last_nb = b - (nch - 1) * per;
+    const size_t wsz = std::max(alb200_mas_workspace_bytes(per, tx, ty), alb200_mas_workspace_bytes(last_nb, tx, ty));
     if (X.cap_ws < wsz) {
         for (int s = 0; s < 2; ++s) {
             if (X.d_ws[s]) ALB_CUDA(cudaFree(X.d_ws[s]));

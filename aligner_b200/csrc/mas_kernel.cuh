@@ -57,6 +57,10 @@ constexpr int kZeroChunk = 7168;   // bytes per zero-fill bulk store (56 x 128; 
 constexpr int kLanePad = 16;       // bytes of skew per lane inside a tile stage
 constexpr int kSkewLag = 1;        // frames lane l trails lane l-1 in the skewed form
 constexpr int kProgDone = 0x3fffffff;
+#ifndef ALB200_DBG_BUILD
+#define ALB200_DBG_BUILD 0
+#endif
+constexpr bool kDbgBuild = ALB200_DBG_BUILD != 0;   // per-warp clock64 stamps (developer aid)
 
 struct WsHeader {       // first 64 bytes of the workspace
     int counter;        // work-stealing cursor (self-resetting)
@@ -70,7 +74,6 @@ struct MasParams {
     void* paths;
     const int32_t* t_xs;
     const int32_t* t_ys;
-    const int32_t* order;       // optional permutation of [0, B): the persistent grid takes utterance order[i] as its i-th work item
     const void* mask;
     int64_t msb, msx, msy;
     int32_t* frame_tok;
@@ -144,8 +147,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// Every wait in this file is bounded: a wrong tensor map or a broken hand-off must surface as a launch error
+// (cudaErrorLaunchFailure at the next synchronisation), never as a hung GPU.  2^26 polls of >= 20 cycles is more than half a
+// second; the longest legitimate wait is a fraction of one utterance's forward pass (milliseconds).
+constexpr uint32_t kSpinLimit = 1u << 26;
+__device__ __forceinline__ void spin_guard(uint32_t& n) { if (++n > kSpinLimit) __trap(); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) { }
+    uint32_t n = 0;
+    while (!mbar_try_wait(bar, parity)) spin_guard(n);
 }
 // 16-byte asynchronous global -> shared copy (LDGSTS.128), L2 only
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -242,6 +251,16 @@ __device__ __forceinline__ int ld_flag(uint32_t a) {
 }
 __device__ __forceinline__ void st_flag(uint32_t a, int v) {
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+// bounded polls (see kSpinLimit): returns the first flag value that is >= need / <= need
+__device__ __forceinline__ int wait_flag_ge(uint32_t a, int need, int seen) {
+    uint32_t n = 0;
+    while (seen < need) { seen = ld_flag(a); spin_guard(n); }
+    return seen;
+}
+__device__ __forceinline__ void wait_flag_le(uint32_t a, int need) {
+    uint32_t n = 0;
+    while (ld_flag(a) > need) spin_guard(n);
 }
 
 // ------------------------------------------------------------------ mask -> length
@@ -640,8 +659,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     const float neg = p.neg;
 
     int item = unit_id;
-    if (p.order != nullptr && item < p.B) item = p.order[item];
-    const bool dbg_on = (p.dbg != nullptr);
+    const bool dbg_on = kDbgBuild && (p.dbg != nullptr);     // compiled out of the shipped library (tools/dbg_timing.py builds its own)
     long long* dbg = dbg_on ? p.dbg + (int64_t)blockIdx.x * (2 * kMaxWarps + 2) * 2 : nullptr;
     bool first_item = true;
     while (item < p.B) {
@@ -855,7 +873,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 S.bprev = 0.f;                                      // x == 0, y == 0: v_prev = 0 (core.pyx:25)
             } else {
                 if (CL && remote_in) wait_remote(y_start + UNIT + 32);
-                else while (ld_flag(in_tail) < y_start + UNIT + (SKEW ? 32 : 0)) { }
+                else wait_flag_ge(in_tail, y_start + UNIT + (SKEW ? 32 : 0), -(1 << 30));
                 if (SKEW) {
                     const float4 b = lds128(bin_addr + (((y_start + 28) & (kRing - 1)) << 2));   // frames y_start-4 .. y_start-1 (+31)
                     S.bprev = b.z; S.bprev1 = b.w;
@@ -876,10 +894,10 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 if (fin == 0) mbar_wait(full0 + 8 * stage, phase);
                 if (dbg_on) c1 = clock64();
                 if (CL && remote_in) wait_remote(y + UNIT + IN_LEAD);
-                while (seen_in < y + UNIT + IN_LEAD) seen_in = ld_flag(in_tail);
+                seen_in = wait_flag_ge(in_tail, y + UNIT + IN_LEAD, seen_in);
                 {
                     const int need = SKEW ? y + UNIT - 32 - kRing : y + UNIT - (kRing - 4);   // our lane 31 is about to overwrite these ring slots
-                    while (seen_cons < need) seen_cons = ld_flag(out_head);
+                    seen_cons = wait_flag_ge(out_head, need, seen_cons);
                 }
                 // read now, needed after this unit (latency hidden): both neighbours' progress.  (Probing the next tile's barrier
                 // here with mbarrier.test_wait was measured: the probe itself costs ~800 cycles per unit -- profiles/r01_notes.md.)
@@ -940,16 +958,16 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         const int top = (crank == 0) ? (t_y - 1) >> 5 : -1;      // cluster: CTA 0 backtracks, the others are done
         if (wid == 0) {
             if (bits_smem) backtrack_walk<2>(bits, TXS, t_x, t_y, top, lane, smem0 + L.off_ring, btTok, btMov, bt_cur_a,
-                                             dbg_on && first_item ? p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4 : nullptr);
+                                             kDbgBuild && dbg_on && first_item ? p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4 : nullptr);
             else           backtrack_walk<4>(bits, TXS, t_x, t_y, top, lane, smem0 + L.off_ring, btTok, btMov, bt_cur_a,
-                                             dbg_on && first_item ? p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4 : nullptr);
+                                             kDbgBuild && dbg_on && first_item ? p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4 : nullptr);
             fence_proxy_async_smem();   // the row windows went through the generic proxy into ring memory that TMA writes next
         } else {
             if (p.frame_tok != nullptr && crank == 0)
                 for (int yy = t_y + (tid - 32); yy < Ty; yy += nthr - 32) p.frame_tok[(int64_t)item * Ty + yy] = -1;
             const int nemit = (nthr >> 5) - 1;                    // every warp but the walker
             for (int blk = top - (wid - 1); blk >= 0; blk -= nemit) {
-                while (ld_flag(bt_cur_a) > blk) { }
+                wait_flag_le(bt_cur_a, blk);
                 const int tokb = btTok[blk];
                 const uint32_t moves = btMov[blk];
                 const int yb = blk << 5;
@@ -972,9 +990,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         // ---- next item
         if (NC > 1 || p.B <= (int)gridDim.x) break;
         if (tid == 0) {
-            int nxt = atomicAdd(&p.ws->counter, 1) + (int)gridDim.x;
-            if (p.order != nullptr && nxt < p.B) nxt = p.order[nxt];
-            misc[0] = nxt;
+            misc[0] = atomicAdd(&p.ws->counter, 1) + (int)gridDim.x;
         }
         __syncthreads();
         item = misc[0];

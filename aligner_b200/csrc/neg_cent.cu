@@ -16,6 +16,7 @@
 //             32 mel frames, keeps their whole text column in shared memory and normalises it there, so the
 //             score matrix is written exactly once.
 #include "../../include/aligner_b200.h"
+#include "alb_opts.h"
 
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -268,7 +269,7 @@ int alb200_neg_cent_gaussian(const float* z, const float* m_p, const float* logs
     if (b > 65535) return nc_fail(ALB200_E_UNSUPPORTED, "neg_cent_gaussian: batch > 65535");
     // default: tensor cores (tcgen05, 3xTF32, fp32 accumulate in TMEM).  ALB200_NC_FFMA=1 selects the CUDA-core kernel below
     // (kept as the fixed-order fp32 cross-check of the tensor-core path, tests/test_neg_cent_gpu.py).
-    if (!getenv("ALB200_NC_FFMA")) return alb200_neg_cent_gaussian_tc(z, m_p, logs_p, out, b, c, tx, ty, stream);
+    if (!alb::opts().nc_ffma) return alb200_neg_cent_gaussian_tc(z, m_p, logs_p, out, b, c, tx, ty, stream);
     dim3 grid((ty + GBN - 1) / GBN, (tx + GBM - 1) / GBM, b);
     gaussian_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, m_p, logs_p, out, c, tx, ty);
     ++alb::g_launches;
@@ -285,7 +286,7 @@ int alb200_neg_cent_ota(const float* queries, const float* keys, const float* pr
     if (b > 65535) return nc_fail(ALB200_E_UNSUPPORTED, "neg_cent_ota: batch > 65535");
     // default: tensor cores; the log-softmax over the text axis is done on the accumulator in tensor memory, which holds
     // 512 tokens.  Longer texts (and ALB200_NC_FFMA=1) take the CUDA-core kernel below.
-    if (tx <= 512 && !getenv("ALB200_NC_FFMA")) return alb200_neg_cent_ota_tc(queries, keys, prior, x_lengths, out, temperature, b, c, tx, ty, stream);
+    if (tx <= 512 && !alb::opts().nc_ffma) return alb200_neg_cent_ota_tc(queries, keys, prior, x_lengths, out, temperature, b, c, tx, ty, stream);
     size_t fixed = ((size_t)c * OBN + (size_t)c * OBX + OBN + 2 * 8 * OBN) * sizeof(float);
     size_t dbytes = (size_t)tx * (OBN + 1) * sizeof(float);
     int optin = 0, dev = 0;

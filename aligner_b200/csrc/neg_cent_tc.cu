@@ -360,11 +360,15 @@ __global__ void __launch_bounds__(256, 1) nc_tc_kernel(const TcParams p)
 template <int MODE>
 static int launch(const TcParams& p, int b, void* stream, const char* who)
 {
-    static thread_local bool configured = false;
-    if (!configured) {
+    // the attribute is per device: remember it per (thread, device)
+    static thread_local bool configured[64] = {false};
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) { snprintf(alb::g_err, sizeof(alb::g_err), "%s: %s", who, cudaGetErrorString(e0)); return ALB200_E_NO_DEVICE; }
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(nc_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) { snprintf(alb::g_err, sizeof(alb::g_err), "%s: %s", who, cudaGetErrorString(e)); return ALB200_E_CUDA; }
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     dim3 grid((p.Ty + BM - 1) / BM, (p.Tx + NMAX - 1) / NMAX, b);
     nc_tc_kernel<MODE><<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(p);

@@ -2,13 +2,17 @@
 
 ``maximum_path(value, mask)`` keeps the reference's signature, return shape,
 dtype rule (``torch.result_type(value, mask)``), device rule (``value.device``)
-and values (exactly 0 / 1), but never leaves the GPU: lengths are derived from
-the mask inside the kernel, the search runs in one sm_100a kernel launch on
-torch's current stream, and the dense path is written directly in the result
-dtype.  PyTorch is only used for device memory and the stream handle.
+and values (exactly 0 / 1).  CUDA tensors never leave the GPU: lengths are
+derived from the mask inside the kernel, the search runs in one sm_100a kernel
+launch on torch's current stream, and the dense path is written directly in the
+result dtype.  CPU tensors (the reference accepts any device, __init__.py:12-14)
+are staged through the host-pointer entry ``alb200_maximum_path_c`` -- the
+search still runs on the B200, there is no CPU implementation of it here.
+PyTorch is only used for memory and the stream handle.
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from .. import _lib
@@ -29,12 +33,18 @@ _MASK_DTYPE = {
 }
 
 _workspaces: dict = {}
+_ws_bytes: dict = {}
 
 
 def _workspace(device: torch.device, stream: int, b: int, tx: int, ty: int) -> torch.Tensor:
     """Zero-initialised scratch, one per (device, stream) so concurrent launches on
     different streams never share the work-stealing counter."""
-    need = int(_lib.lib.alb200_mas_workspace_bytes(b, tx, ty))
+    skey = (device.index, b, tx, ty)
+    need = _ws_bytes.get(skey)
+    if need is None:                      # the sizing call probes several kernel configurations: once per shape
+        if len(_ws_bytes) > 4096:
+            _ws_bytes.clear()
+        need = _ws_bytes[skey] = int(_lib.lib.alb200_mas_workspace_bytes(b, tx, ty))
     key = (device.index, stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
@@ -51,8 +61,6 @@ def _prep_value(value: torch.Tensor) -> torch.Tensor:
     them on load, exactly like .astype(np.float32) in the reference, __init__.py:14); anything else is promoted here."""
     if value.dim() != 3:
         raise ValueError("value must be [b, t_x, t_y], got %s" % (tuple(value.shape),))
-    if not value.is_cuda:
-        raise RuntimeError("aligner_b200 runs on sm_100a only: value must be a CUDA tensor (no CPU fallback)")
     v = value.detach()
     if v.dtype not in _VALUE_DTYPE:
         v = v.to(torch.float32)
@@ -69,19 +77,41 @@ def _launch(v: torch.Tensor, args_after_value: tuple) -> None:
     _lib.check(rc)
 
 
-def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, return_durations: bool = False):
+def _maximum_path_host(value: torch.Tensor, mask: torch.Tensor, dtype: torch.dtype, apply_mask: bool, return_durations: bool):
+    """CPU tensors: what the reference's own staging does (__init__.py:11-21), with the compiled core replaced by the
+    host-pointer entry of the library (values go to the B200 in chunks, the token of every frame comes back)."""
+    if apply_mask:
+        value = value * mask                                           # __init__.py:11
+    v = np.ascontiguousarray(value.detach().to(torch.float32).numpy())  # __init__.py:14
+    path = np.zeros(v.shape, np.int32)                                 # __init__.py:15
+    m = mask.detach()
+    if m.dtype == torch.bfloat16:
+        m = m.float()
+    m = m.numpy()                                                      # __init__.py:16
+    t_x = np.ascontiguousarray(m.sum(1)[:, 0].astype(np.int32))        # __init__.py:18
+    t_y = np.ascontiguousarray(m.sum(2)[:, 0].astype(np.int32))        # __init__.py:19
+    if v.size:
+        maximum_path_c(path, v, t_x, t_y)                              # __init__.py:20
+    out = torch.from_numpy(path).to(dtype=dtype)                       # __init__.py:21
+    return (out, torch.from_numpy(path.sum(-1).astype(np.int32))) if return_durations else out
+
+
+def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, return_durations: bool = False, apply_mask: bool = False):
     """Monotonic alignment search.  Reference: monotonic_align/__init__.py:6-21.
 
-    value: [b, t_x, t_y] scores (log-likelihoods), any float dtype, on a B200.
+    value: [b, t_x, t_y] scores (log-likelihoods), any float dtype, any device (the search runs on the B200).
     mask:  [b, t_x, t_y] outer product of the text and mel prefix masks, any dtype.
     Returns the 0/1 path [b, t_x, t_y] in ``torch.result_type(value, mask)`` on
     ``value.device``; inputs are not modified; no autograd history.
 
     Differences from the reference, all supersets: bf16 and non-contiguous inputs
     are accepted; ``return_durations=True`` also returns ``path.sum(-1)`` as int32.
-    The mask must be prefix-shaped (ones in [0,t_x) x [0,t_y), zeros elsewhere),
-    which is what every caller of the reference builds; only mask[:, :, 0] and
-    mask[:, 0, :] are read.
+    For a prefix-shaped mask (ones in [0,t_x) x [0,t_y), zeros elsewhere -- what every
+    caller of the reference builds) ``value * mask`` (__init__.py:11) is the identity on
+    every cell the search reads, so only mask[:, :, 0] and mask[:, 0, :] are read and the
+    product is skipped.  ``apply_mask=True`` performs the multiplication first (one
+    extra elementwise pass on value.device), which reproduces the reference for
+    arbitrary masks too.
     """
     if mask.shape != value.shape:
         raise ValueError("mask shape %s != value shape %s" % (tuple(mask.shape), tuple(value.shape)))
@@ -90,6 +120,12 @@ def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, return_durations: b
     dtype = torch.result_type(value, mask)
     if dtype not in _ONE or mask.dtype not in _MASK_DTYPE:
         raise TypeError("unsupported dtype combination %s / %s" % (value.dtype, mask.dtype))
+    if value.dim() != 3:
+        raise ValueError("value must be [b, t_x, t_y], got %s" % (tuple(value.shape),))
+    if not value.is_cuda:
+        return _maximum_path_host(value, mask, dtype, apply_mask, return_durations)
+    if apply_mask:
+        value = value.detach() * mask.detach()
     v = _prep_value(value)
     b, tx, ty = v.shape
     esize, one = _ONE[dtype]
@@ -102,7 +138,7 @@ def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, return_durations: b
         ws = _workspace(v.device, stream, b, tx, ty)
         m = mask.detach()
         sb, sx, sy = m.stride()
-        _launch(v, (None, None, m.data_ptr(), _MASK_DTYPE[m.dtype], sb, sx, sy, None,
+        _launch(v, (None, None, m.data_ptr(), _MASK_DTYPE[m.dtype], sb, sx, sy,
                     path.data_ptr(), esize, one, 1, None, dur.data_ptr() if dur is not None else None, None,
                     b, tx, ty, -1e9, ws.data_ptr(), ws.numel(), stream))
     return (path, dur) if return_durations else path
@@ -135,7 +171,7 @@ def maximum_path_vits(neg_cent: torch.Tensor, mask: torch.Tensor) -> torch.Tenso
             m = mask.detach()
             sb, sy, sx = m.stride()                              # mask is [b, t_mel, t_text]; the kernel wants (b, text, mel) strides
             rc = _lib.lib.alb200_mas_device_ex(v.data_ptr(), _lib.F32 | _lib.LAYOUT_VITS, None, None, m.data_ptr(), _MASK_DTYPE[m.dtype],
-                                               sb, sx, sy, None, path.data_ptr(), esize, one, 1, None, None, None,
+                                               sb, sx, sy, path.data_ptr(), esize, one, 1, None, None, None,
                                                b, tx, ty, -1e9, ws.data_ptr(), ws.numel(), stream)
         if rc == 0:
             return path
@@ -147,13 +183,11 @@ def maximum_path_vits(neg_cent: torch.Tensor, mask: torch.Tensor) -> torch.Tenso
 def maximum_path_lengths(value: torch.Tensor, x_lengths: torch.Tensor, y_lengths: torch.Tensor, *,
                          out_dtype: torch.dtype | None = None, dense: bool = True,
                          return_durations: bool = False, return_frame_tokens: bool = False,
-                         max_neg_val: float = -1e9, order=None):
+                         max_neg_val: float = -1e9):
     """Mask-free entry: lengths given directly as int32 [b] CUDA tensors.
-    Returns a dict with any of 'path', 'durations' (int32 [b,t_x]), 'frame_tokens' (int32 [b,t_y], -1 past t_y).
-
-    order: None (batch order), an int32 [b] CUDA permutation, or "lpt" = longest utterance first (descending
-    t_x*t_y, computed on the device): the persistent grid then starts the expensive items first, which shortens
-    the tail of a mixed-length batch.  The result does not depend on it."""
+    Returns a dict with any of 'path', 'durations' (int32 [b,t_x]), 'frame_tokens' (int32 [b,t_y], -1 past t_y)."""
+    if not value.is_cuda:
+        raise RuntimeError("maximum_path_lengths takes CUDA tensors (CPU tensors: maximum_path, or maximum_path_c with numpy arrays)")
     v = _prep_value(value)
     b, tx, ty = v.shape
     dtype = out_dtype or value.dtype
@@ -170,15 +204,7 @@ def maximum_path_lengths(value: torch.Tensor, x_lengths: torch.Tensor, y_lengths
         if b > 0 and tx > 0 and ty > 0:
             stream = torch.cuda.current_stream(v.device).cuda_stream
             ws = _workspace(v.device, stream, b, tx, ty)
-            if isinstance(order, str):
-                if order != "lpt":
-                    raise ValueError("order must be None, 'lpt' or an int32 permutation tensor")
-                order = torch.argsort(xl.to(torch.int64) * yl.to(torch.int64), descending=True, stable=True).to(torch.int32)
-            elif order is not None:
-                order = order.to(device=v.device, dtype=torch.int32).contiguous()
-                if order.numel() != b:
-                    raise ValueError("order must hold a permutation of range(b)")
-            _launch(v, (xl.data_ptr(), yl.data_ptr(), None, 0, 0, 0, 0, order.data_ptr() if order is not None else None,
+            _launch(v, (xl.data_ptr(), yl.data_ptr(), None, 0, 0, 0, 0,
                         path.data_ptr() if dense else None, esize, one, 1,
                         ftok.data_ptr() if ftok is not None else None, dur.data_ptr() if dur is not None else None, None,
                         b, tx, ty, max_neg_val, ws.data_ptr(), ws.numel(), stream))

@@ -30,16 +30,16 @@ FLAGS = [
 
 
 def _deps(src: Path) -> list[Path]:
-    return [src] + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "aligner_b200.h"]
+    return [src] + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [PKG.parent / "include" / "aligner_b200.h"]
 
 
 def _stale(out: Path, deps: list[Path]) -> bool:
     return (not out.exists()) or any(d.exists() and d.stat().st_mtime > out.stat().st_mtime for d in deps)
 
 
-def _compile(src: Path, verbose: bool) -> Path:
-    obj = OBJ / (src.stem + ".o")
-    cmd = [NVCC, *FLAGS, "-c", str(src), "-o", str(obj)]
+def _compile(src: Path, verbose: bool, extra=(), suffix: str = "") -> Path:
+    obj = OBJ / (src.stem + suffix + ".o")
+    cmd = [NVCC, *FLAGS, *extra, "-c", str(src), "-o", str(obj)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)
@@ -66,6 +66,22 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_dbg() -> Path:
+    """Developer variant with the per-warp clock64 stamps compiled in (tools/dbg_timing.py): libaligner_b200_dbg.so."""
+    srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+    OBJ.mkdir(exist_ok=True)
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        objs = list(ex.map(lambda s: _compile(s, False, ("-DALB200_DBG_BUILD=1",), "_dbg"), srcs))
+    out = PKG / "libaligner_b200_dbg.so"
+    proc = subprocess.run([NVCC, "-shared", "-o", str(out), *map(str, objs), "-lcudart"], capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (proc.stdout, proc.stderr))
+    return out
+
+
 if __name__ == "__main__":
+    if "--dbg" in sys.argv:
+        print(build_dbg())
+        sys.exit(0)
     out = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(out)

@@ -46,6 +46,13 @@ const char *alb200_last_error(void);
 /* "aligner_b200 <version> sm_100a" */
 const char *alb200_version(void);
 
+/* Tuning / test options.  They are read from the environment once, when the library is first used (ALB200_FORCE,
+ * ALB200_LATENCY_MAX_B, ALB200_TMAP_PROMO, ALB200_NO_TAIL_BOX, ALB200_FORCE_UNALIGNED, ALB200_DBG, ALB200_NC_FFMA,
+ * ALB200_NC_V1), and can be changed afterwards with this call: name = the variable without the prefix, lower case
+ * ("force", "latency_max_b", ...); value NULL or "" restores the default.  No launch path reads the environment.
+ * Process-wide; not meant to be changed while another thread is launching. */
+int alb200_set_option(const char *name, const char *value);
+
 /* ------------------------------------------------------------------------
  * Monotonic alignment search, device pointers, asynchronous on `stream`.
  *
@@ -80,17 +87,7 @@ int alb200_mas_device(const float *values, const int32_t *t_xs, const int32_t *t
                       int b, int tx, int ty, float max_neg_val,
                       void *workspace, size_t workspace_bytes, void *stream);
 
-/* Same as alb200_mas_device with a processing order: `order` is an int32 [b] device array holding a permutation
- * of 0..b-1; the persistent grid takes utterance order[i] as its i-th work item.  Results are identical for any
- * order (utterances are independent, core.pyx:44-45); handing over the longest utterances first (descending
- * t_x*t_y) shortens the tail of a mixed-length batch.  NULL = batch order. */
-int alb200_mas_device_ordered(const float *values, const int32_t *t_xs, const int32_t *t_ys, const int32_t *order,
-                              void *paths, int path_elem_size, uint64_t path_one, int zero_fill,
-                              int32_t *frame_tok, int32_t *durations,
-                              int b, int tx, int ty, float max_neg_val,
-                              void *workspace, size_t workspace_bytes, void *stream);
-
-/* The general device entry: every option of the three entries around it, plus the score element type.
+/* The general device entry: every option of the two entries around it, plus the score element type.
  *   value_dtype  ALB200_F32, ALB200_F16 or ALB200_BF16.  Half-precision scores are promoted to fp32 as they are loaded,
  *                which is exactly the reference's `.astype(np.float32)` (monotonic_align/__init__.py:14): the path is
  *                bit-identical to the reference run on the promoted values, and the kernel reads 2 instead of 4 bytes
@@ -100,11 +97,9 @@ int alb200_mas_device_ordered(const float *values, const int32_t *t_xs, const in
  *   lengths      either (t_xs, t_ys) or mask (+ strides in elements), as in alb200_mas_device / _masked.
  *   layout       value_dtype | ALB200_LAYOUT_VITS: scores and path are [b, t_mel, t_text] (mask strides are still given
  *                as (b, text, mel)).  Native for fp32 in the latency regime with <= 4 rows per lane and t_x % 4 == 0;
- *                otherwise ALB200_E_UNSUPPORTED (the Python layer then transposes on the device).
- *   order        optional, as in alb200_mas_device_ordered. */
+ *                otherwise ALB200_E_UNSUPPORTED (the Python layer then transposes on the device). */
 int alb200_mas_device_ex(const void *values, int value_dtype, const int32_t *t_xs, const int32_t *t_ys,
                          const void *mask, int mask_dtype, int64_t mask_stride_b, int64_t mask_stride_x, int64_t mask_stride_y,
-                         const int32_t *order,
                          void *paths, int path_elem_size, uint64_t path_one, int zero_fill,
                          int32_t *frame_tok, int32_t *durations, int32_t *lens_out,
                          int b, int tx, int ty, float max_neg_val,
@@ -164,7 +159,10 @@ void alb200_last_transfer_bytes(uint64_t *h2d, uint64_t *d2h);
  * The reference snapshot has no code for these (its MoBo/RoMo/OTA branches are not in the
  * tree, README.md:9-25); they implement the published formulas of the projects it links to
  * and produce the layout the reference API documents: [b, t_text, t_mel], t_mel contiguous
- * (monotonic_align/__init__.py:8-9).  fp32 in, fp32 out, fp32 accumulation in a fixed order.
+ * (monotonic_align/__init__.py:8-9).  fp32 in, fp32 out.  Default path: 5th-generation tensor cores (tcgen05) with every
+ * operand split into two half-width parts (three products, fp32 accumulation in tensor memory) -- within 1e-5 of the fp64
+ * value relative to the largest |score| of the utterance; the Gaussian score is formed as the contraction plus a per-token
+ * term, the OTA distance as |q|^2 + |k|^2 - 2 q.k.  Option "nc_ffma" selects fixed-order fp32 FFMA kernels instead.
  *
  * Gaussian prior (Glow-TTS / VITS `neg_cent1..4`):
  *   out[b,x,y] = sum_c log N(z[b,c,y]; m_p[b,c,x], exp(logs_p[b,c,x])^2)

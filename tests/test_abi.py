@@ -69,8 +69,17 @@ def test_fails_loudly_without_gpu():
                        np.array([2], np.int32), np.array([3], np.int32))
     assert ei.value.code == _lib.E_NO_DEVICE
     import aligner_b200.monotonic_align as ma
-    with pytest.raises(RuntimeError):
+    with pytest.raises(_lib.AlignerB200Error) as ei:          # CPU tensors are staged to the GPU: without one this fails loudly too
         ma.maximum_path(torch.zeros(1, 2, 3), torch.ones(1, 2, 3))
+    assert ei.value.code == _lib.E_NO_DEVICE
+
+
+def test_options_are_validated():
+    from aligner_b200 import _lib
+    _lib.set_option("force", "2,32,3,1,1")
+    _lib.set_option("force", None)
+    with pytest.raises(_lib.AlignerB200Error):
+        _lib.set_option("no_such_option", "1")
 
 
 def test_host_entry_validates_like_the_cython_buffer_protocol():

@@ -20,6 +20,35 @@ def ma():
     return m
 
 
+@pytest.fixture
+def option():
+    """Set library tuning options (alb200_set_option) for one test; defaults are restored afterwards."""
+    touched = []
+
+    def _set(name, value):
+        _lib.set_option(name, value)
+        touched.append(name)
+    yield _set
+    for name in touched:
+        _lib.set_option(name, None)
+
+
+def seed_of(*parts):
+    """Deterministic across processes (unlike hash() of strings, which PYTHONHASHSEED randomises)."""
+    import zlib
+    return zlib.crc32(repr(parts).encode()) & 0x7fffffff
+
+
+def reference_paths(values, t_x, t_y):
+    """The reference's own compiled core.pyx (oracle/_ref, prebuilt, travels to the GPU box)."""
+    ref = oracle.load_reference_core("omp") or oracle.load_reference_core("serial")
+    if ref is None:
+        pytest.skip("oracle/_ref is not built")
+    p = np.zeros(values.shape, np.int32)
+    ref.maximum_path_c(p, values.copy(), np.ascontiguousarray(t_x, np.int32), np.ascontiguousarray(t_y, np.int32))
+    return p
+
+
 def oracle_paths(values, t_x, t_y):
     p = np.zeros(values.shape, np.int32)
     oracle.maximum_path_c_port(p, values.copy(), np.ascontiguousarray(t_x, np.int32), np.ascontiguousarray(t_y, np.int32), omp=True)
@@ -68,11 +97,11 @@ FORCES = [None, "1,32,2,1,0", "1,32,3,0,1", "2,16,2,1,0", "2,32,4,0,1", "2,32,2,
 
 @pytest.mark.parametrize("force", FORCES)
 @pytest.mark.parametrize("kind", ["gauss", "ties", "sentinel", "negative"])
-def test_differential_small(ma, monkeypatch, force, kind):
+def test_differential_small(ma, option, force, kind):
     if force:
-        monkeypatch.setenv("ALB200_FORCE", force)
+        option("force", force)
     rmax = 4 * 32 * int(force.split(",")[0]) if force else 300         # a forced rows-per-lane caps t_x at 4 compute warps
-    rng = np.random.default_rng(abs(hash((force, kind))) % (2 ** 31))
+    rng = np.random.default_rng(seed_of(force, kind))
     for trial in range(6):
         b = int(rng.integers(1, 9))
         tx = int(rng.integers(1, min(300, rmax)))
@@ -91,7 +120,7 @@ def test_differential_small(ma, monkeypatch, force, kind):
                                           ((2, 600, 700), False)])      # cluster shapes
 def test_vits_layout_entry(ma, shape, native):
     """[b, t_mel, t_text] in and out, as VITS calls it; same search (its core indexes value[y, x])."""
-    rng = np.random.default_rng(abs(hash(shape)) % (2 ** 31))
+    rng = np.random.default_rng(seed_of("vits", shape))
     b, tx, ty = shape
     values = make_values(rng, "gauss", (b, tx, ty))
     t_x, t_y = random_lengths(rng, b, tx, ty)
@@ -120,7 +149,7 @@ def test_vits_layout_entry(ma, shape, native):
                                           ((6, 150, 403), False),     # latency regime + unaligned rows: promoted on the device
                                           ((4, 700, 900), False)])    # latency regime, > 4 rows per lane: promoted on the device
 def test_half_precision_scores(ma, dtype, shape, native):
-    rng = np.random.default_rng(abs(hash((str(dtype), shape))) % (2 ** 31))
+    rng = np.random.default_rng(seed_of(str(dtype), shape))
     b, tx, ty = shape
     v = torch.from_numpy(make_values(rng, "gauss", shape)).cuda().to(dtype)
     t_x, t_y = random_lengths(rng, b, tx, ty)
@@ -138,26 +167,12 @@ def test_half_precision_scores(ma, dtype, shape, native):
     stream = torch.cuda.current_stream().cuda_stream
     ws = ma._workspace(v.device, stream, b, tx, ty)
     rc = _lib.lib.alb200_mas_device_ex(v.data_ptr(), _lib.F16 if dtype == torch.float16 else _lib.BF16, xl.data_ptr(), yl.data_ptr(),
-                                       None, 0, 0, 0, 0, None, path.data_ptr(), 4, 1, 1, None, None, None, b, tx, ty, -1e9,
+                                       None, 0, 0, 0, 0, path.data_ptr(), 4, 1, 1, None, None, None, b, tx, ty, -1e9,
                                        ws.data_ptr(), ws.numel(), stream)
     torch.cuda.synchronize()
     assert rc == (0 if native else _lib.E_UNSUPPORTED)
     if native:
         assert np.array_equal(path.cpu().numpy(), want)
-
-
-def test_processing_order_does_not_change_results(ma):
-    """alb200_mas_device_ordered: any permutation (and the built-in longest-first order) gives the batch-order result."""
-    rng = np.random.default_rng(11)
-    b, tx, ty = 700, 60, 160                     # more utterances than resident CTAs: the work cursor is exercised
-    values = make_values(rng, "gauss", (b, tx, ty))
-    t_x, t_y = random_lengths(rng, b, tx, ty)
-    want = oracle_paths(values, t_x, t_y)
-    v, xl, yl = torch.from_numpy(values).cuda(), torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda()
-    for order in ("lpt", torch.from_numpy(rng.permutation(b).astype(np.int32)).cuda()):
-        out = ma.maximum_path_lengths(v, xl, yl, out_dtype=torch.int32, return_durations=True, order=order)
-        assert np.array_equal(out["path"].cpu().numpy(), want)
-        assert np.array_equal(out["durations"].cpu().numpy(), want.sum(-1))
 
 
 def test_midsize_batch_runs_the_skewed_form_persistently(ma):
@@ -179,7 +194,7 @@ def test_midsize_batch_runs_the_skewed_form_persistently(ma):
                                    (150, 513, 600),      # more clusters than fit: single-CTA throughput form
                                    (5, 33, 33), (2, 2047, 2050)])    # square; unaligned rows with 8 compute warps
 def test_extreme_shapes(ma, shape):
-    rng = np.random.default_rng(abs(hash(shape)) % (2 ** 31))
+    rng = np.random.default_rng(seed_of("extreme", shape))
     b, tx, ty = shape
     values = make_values(rng, "gauss", shape)
     t_x, t_y = random_lengths(rng, b, tx, ty)
@@ -190,9 +205,9 @@ def test_extreme_shapes(ma, shape):
 # ------------------------------------------------------------------ cluster mode: one utterance split over the CTAs of a cluster
 @pytest.mark.parametrize("force,txmax", [("1,32,3,0,1,2", 256), ("2,32,3,0,1,2", 512), ("2,32,2,0,1,4", 1024), ("1,32,4,0,1,8", 1024),
                                          ("3,32,2,0,1,3", 1152)])
-def test_cluster_mode_forced(ma, monkeypatch, force, txmax):
-    monkeypatch.setenv("ALB200_FORCE", force)
-    rng = np.random.default_rng(abs(hash(force)) % (2 ** 31))
+def test_cluster_mode_forced(ma, option, force, txmax):
+    option("force", force)
+    rng = np.random.default_rng(seed_of("cluster", force))
     for trial in range(3):
         b = int(rng.integers(1, 6))
         tx = int(rng.integers(txmax // 2, txmax + 1))
@@ -213,20 +228,18 @@ def test_cluster_mode_is_the_default_for_long_text(ma):
     t_x, t_y = random_lengths(rng, b, tx, ty)                          # short items leave whole CTAs of a cluster idle
     t_x[0], t_y[0] = 7, 9
     check_against_oracle(ma, values, t_x, t_y)
-    # the reference API (lengths from the mask, in every CTA of the cluster) and an explicit processing order
+    # the reference API (lengths from the mask, in every CTA of the cluster)
     want = oracle_paths(values, t_x, t_y)
     v = torch.from_numpy(values).cuda()
     got = ma.maximum_path(v, torch.from_numpy(prefix_mask_np(t_x, t_y, tx, ty)).cuda())
     assert np.array_equal(got.cpu().numpy(), want.astype(np.float32))
-    out = ma.maximum_path_lengths(v, torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda(), out_dtype=torch.int32, order="lpt")
-    assert np.array_equal(out["path"].cpu().numpy(), want)
     assert "cluster=1" in _lib.describe(148, tx, ty)                   # not when the clusters would not all be resident
 
 
 @pytest.mark.parametrize("skew", ["0", "1"])
-def test_unaligned_loader_forced(ma, monkeypatch, skew):
-    monkeypatch.setenv("ALB200_FORCE_UNALIGNED", "1")
-    monkeypatch.setenv("ALB200_FORCE", "2,32,2,1," + skew)
+def test_unaligned_loader_forced(ma, option, skew):
+    option("force_unaligned", "1")
+    option("force", "2,32,2,1," + skew)
     rng = np.random.default_rng(77)
     values = make_values(rng, "gauss", (5, 150, 400))
     t_x, t_y = random_lengths(rng, 5, 150, 400)
@@ -234,8 +247,8 @@ def test_unaligned_loader_forced(ma, monkeypatch, skew):
 
 
 @pytest.mark.parametrize("skew", ["0", "1"])
-def test_both_forward_forms_on_ragged_batch(ma, monkeypatch, skew):
-    monkeypatch.setenv("ALB200_FORCE", "2,32,3,1," + skew)
+def test_both_forward_forms_on_ragged_batch(ma, option, skew):
+    option("force", "2,32,3,1," + skew)
     rng = np.random.default_rng(78)
     values = make_values(rng, "ties", (40, 200, 600))
     t_x, t_y = random_lengths(rng, 40, 200, 600)
@@ -334,7 +347,7 @@ def test_api_edge_shapes(ma):
     v = torch.randn(2, 1, 1).cuda()
     assert torch.equal(ma.maximum_path(v, torch.ones_like(v)), torch.ones_like(v))
     with pytest.raises(RuntimeError):
-        ma.maximum_path(torch.zeros(1, 2, 3), torch.ones(1, 2, 3))        # CPU tensors: no fallback
+        ma.maximum_path_lengths(torch.zeros(1, 2, 3), torch.tensor([2]), torch.tensor([3]))   # the extension entry is CUDA only
     with pytest.raises(ValueError):
         ma.maximum_path(torch.zeros(1, 2, 3).cuda(), torch.ones(1, 2, 4).cuda())
 
@@ -385,3 +398,143 @@ def test_host_maximum_path_c(ma):
     paths = np.zeros((1, 2, 3), np.int32)
     maximum_path_c(paths=paths, values=np.zeros((1, 2, 3), np.float32), t_xs=np.array([2], np.int32), t_ys=np.array([3], np.int32), max_neg_val=-1e9)
     assert paths.sum() == 3
+
+
+# ------------------------------------------------------------------ CPU tensors: the reference accepts any device (__init__.py:12-14,21)
+def test_golden_vectors_on_cpu_tensors(ma, golden):
+    """CPU tensors are staged through alb200_maximum_path_c (the search still runs on the B200) and come back on the CPU."""
+    for name, c in golden.items():
+        value, mask = torch.from_numpy(c["value"]), torch.from_numpy(c["mask"])
+        v0 = value.clone()
+        n0 = _lib.launch_count()
+        got = ma.maximum_path(value, mask)
+        assert got.device.type == "cpu" and str(got.dtype) == str(c["path_dtype"]) and got.shape == value.shape, name
+        assert torch.equal(value, v0), "input mutated: " + name
+        assert np.array_equal(got.numpy(), c["path"]), name
+        if value.numel() and c["path"].any():
+            assert _lib.launch_count() > n0, "no kernel launched for " + name
+
+
+def test_apply_mask_reproduces_the_reference_for_arbitrary_masks(ma):
+    """A mask that is not prefix-shaped: the reference multiplies first (__init__.py:11); apply_mask=True does the same."""
+    rng = np.random.default_rng(36)
+    b, tx, ty = 3, 24, 60
+    value = torch.from_numpy(make_values(rng, "gauss", (b, tx, ty)))
+    mask = torch.from_numpy(prefix_mask_np(np.array([24, 20, 11]), np.array([60, 44, 30]), tx, ty))
+    mask[:, 3:6, 10:20] = 0                                   # holes inside the band
+    want = oracle.maximum_path_port(value, mask)
+    for dev in ("cuda", "cpu"):
+        got = ma.maximum_path(value.to(dev), mask.to(dev), apply_mask=True)
+        assert torch.equal(got.cpu(), want), dev
+
+
+# ------------------------------------------------------------------ NaN / +-inf scores, against the reference's own compiled core
+# Select semantics under test (core.c:19384-19391, 19444): `v_prev > v_cur ? v_prev : v_cur` -- a NaN v_prev is dropped, a NaN
+# v_cur propagates; the backtrack's `<` is false on NaN.  OTA scores legitimately hold -inf rows (text padding).
+NONFINITE_FORMS = [None, "2,32,3,1,0", "2,32,3,1,1", "1,32,3,0,1", "4,16,2,1,0", "4,32,2,1,1", "8,16,2,0,0", "2,32,3,0,1,2", "1,32,3,0,1,4"]
+
+
+@pytest.mark.parametrize("force", NONFINITE_FORMS)
+@pytest.mark.parametrize("kind", ["nan", "pinf", "ninf", "ota_rows", "mixed"])
+def test_nonfinite_scores_match_the_compiled_reference(ma, option, force, kind):
+    if force:
+        option("force", force)
+    parts = [int(q) for q in force.split(",")] if force else None
+    nc = parts[5] if parts and len(parts) > 5 else 1
+    rmax = 4 * 32 * parts[0] * nc if parts else 300
+    rng = np.random.default_rng(seed_of("nonfinite", force, kind))
+    for trial in range(4):
+        b = int(rng.integers(1, 7))
+        tx = int(rng.integers(max(2, rmax // 2 if nc > 1 else 2), min(300 if nc == 1 else rmax, rmax) + 1))
+        ty = (int(rng.integers(tx, tx + 400)) + 3) // 4 * 4
+        values = make_values(rng, "gauss", (b, tx, ty))
+        t_x, t_y = random_lengths(rng, b, tx, ty, full=(trial == 0))
+        n = max(1, values.size // 200)
+        flat = values.reshape(-1)
+        idx = rng.choice(values.size, n, replace=False)
+        if kind == "nan":
+            flat[idx] = np.nan
+        elif kind == "pinf":
+            flat[idx] = np.inf
+        elif kind == "ninf":
+            flat[idx] = -np.inf
+        elif kind == "ota_rows":                       # whole token rows at -inf, like OTA text padding inside the tensor
+            for i in range(b):
+                values[i, rng.integers(0, tx, max(1, tx // 10))] = -np.inf
+        else:
+            flat[idx] = rng.choice(np.array([np.nan, np.inf, -np.inf], np.float32), n)
+        want = reference_paths(values, t_x, t_y)
+        got, dur, _ = gpu_paths(ma, values, t_x, t_y)
+        bad = np.argwhere((got != want).reshape(b, -1).any(1)).ravel()
+        assert bad.size == 0, "items differ from the compiled reference: %s (t_x=%s t_y=%s)" % (bad[:8], t_x[bad[:8]], t_y[bad[:8]])
+        assert (dur == want.sum(-1)).all()
+        assert np.array_equal(want, oracle_paths(values, t_x, t_y))     # and the C restatement agrees with the reference here too
+
+
+def test_compiled_reference_directly_on_baseline_shape(ma):
+    """GPU path vs oracle/_ref itself (not the restatement) at the bench shape, ragged."""
+    rng = np.random.default_rng(1234 + 2)
+    b, tx, ty = 64, 200, 1000
+    values = make_values(rng, "gauss", (b, tx, ty))
+    t_x, t_y = random_lengths(rng, b, tx, ty)
+    t_x[:8], t_y[:8] = tx, ty
+    want = reference_paths(values, t_x, t_y)
+    got, dur, _ = gpu_paths(ma, values, t_x, t_y)
+    assert np.array_equal(got, want) and (dur == want.sum(-1)).all()
+
+
+# ------------------------------------------------------------------ config 5 through the shard planner, on one GPU
+def test_c5_ragged_batch_through_balance_shards(ma):
+    """A C5-shaped batch is split with balance_shards into 1/2/4/8 shards, the shards run one after the other on this GPU,
+    and the reassembled durations / frame tokens equal the unsharded run (utterance independence, core.pyx:44-45)."""
+    from aligner_b200 import sharding
+    rng = np.random.default_rng(1239)
+    b, tx, ty = 384, 400, 2000
+    t_x = rng.integers(50, tx + 1, b).astype(np.int32)
+    t_y = np.array([rng.integers(max(200, t_x[i]), ty + 1) for i in range(b)], np.int32)
+    g = torch.Generator(device="cuda").manual_seed(1239)
+    values = torch.randn(b, tx, ty, generator=g, device="cuda")
+    xl, yl = torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda()
+    whole = ma.maximum_path_lengths(values, xl, yl, dense=False, return_durations=True, return_frame_tokens=True)
+    for world in (2, 4, 8):
+        shards = sharding.balance_shards(t_x, t_y, world)
+        loads = sharding.shard_loads(t_x, t_y, shards)
+        assert loads.max() - loads.min() <= sharding.item_cost(t_x, t_y).max()
+        dur = torch.full_like(whole["durations"], -7)
+        ftok = torch.full_like(whole["frame_tokens"], -7)
+        for s in shards:
+            idx = torch.from_numpy(s).cuda()
+            out = ma.maximum_path_lengths(values[idx], xl[idx], yl[idx], dense=False, return_durations=True, return_frame_tokens=True)
+            dur[idx] = out["durations"]
+            ftok[idx] = out["frame_tokens"]
+        assert torch.equal(dur, whole["durations"]) and torch.equal(ftok, whole["frame_tokens"]), world
+    sample = rng.choice(b, 12, replace=False)
+    want = oracle_paths(values[sample].cpu().numpy(), t_x[sample], t_y[sample])
+    assert np.array_equal(whole["durations"][sample].cpu().numpy(), want.sum(-1))
+
+
+# ------------------------------------------------------------------ soak: the flag hand-offs between warps, 10^4 launches
+def test_soak_ten_thousand_launches(ma):
+    """Random small shapes in every regime, 10^4 launches: every result is compared with the C restatement (durations and
+    frame tokens) -- a lost or reordered hand-off between warps (boundary ring, walker -> emitters) would show up here."""
+    rng = np.random.default_rng(20261017)
+    pool = []
+    for _ in range(40):
+        b = int(rng.choice([1, 3, 8, 40, 180, 400]))
+        tx = int(rng.integers(1, 260))
+        ty = int(rng.integers(tx, tx + 300))
+        if rng.integers(0, 2):
+            ty = (ty + 3) // 4 * 4
+        values = make_values(rng, ["gauss", "ties"][int(rng.integers(0, 2))], (b, tx, ty))
+        t_x, t_y = random_lengths(rng, b, tx, ty)
+        _, ftok = oracle.mas_bits_port(values, t_x, t_y, omp=True)
+        for i in range(b):
+            ftok[i, t_y[i]:] = -1
+        pool.append((torch.from_numpy(values).cuda(), torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda(), torch.from_numpy(ftok).cuda()))
+    bad = torch.zeros((), dtype=torch.int64, device="cuda")
+    n = 10000
+    for it in range(n):
+        v, xl, yl, want = pool[int(rng.integers(0, len(pool)))]
+        out = ma.maximum_path_lengths(v, xl, yl, dense=False, return_frame_tokens=True)
+        bad += (out["frame_tokens"] != want).any().long()
+    assert int(bad.item()) == 0, "%d of %d launches differed from the oracle" % (int(bad.item()), n)

@@ -64,15 +64,19 @@ def test_ota_matches_fp64(nc, b, c, tx, ty, with_prior, with_len):
 
 
 @pytest.mark.parametrize("b,c,tx,ty", [(2, 192, 200, 1000), (2, 50, 600, 300), (1, 7, 513, 129)])
-def test_tensor_core_and_cuda_core_paths_agree(nc, monkeypatch, b, c, tx, ty):
+def test_tensor_core_and_cuda_core_paths_agree(nc, b, c, tx, ty):
     """The tcgen05 kernels (default) against the fixed-order FFMA kernels (ALB200_NC_FFMA=1): two independent implementations."""
     g = torch.Generator(device="cuda").manual_seed(7 + tx)
     z = torch.randn(b, c, ty, generator=g, device="cuda")
     m = torch.randn(b, c, tx, generator=g, device="cuda")
     logs = torch.rand(b, c, tx, generator=g, device="cuda") * 1.5 - 1.0
     tc_g, tc_o = nc.gaussian_neg_cent(z, m, logs), nc.ota_log_prob(z, m, 0.0005)
-    monkeypatch.setenv("ALB200_NC_FFMA", "1")
-    ff_g, ff_o = nc.gaussian_neg_cent(z, m, logs), nc.ota_log_prob(z, m, 0.0005)
+    from aligner_b200 import _lib
+    _lib.set_option("nc_ffma", "1")
+    try:
+        ff_g, ff_o = nc.gaussian_neg_cent(z, m, logs), nc.ota_log_prob(z, m, 0.0005)
+    finally:
+        _lib.set_option("nc_ffma", None)
     assert (tc_g - ff_g).abs().max() <= TOL * ff_g.abs().max()
     assert (tc_o - ff_o).abs().max() <= TOL * ff_o.abs().max()
 

@@ -10,7 +10,6 @@ import aligner_b200.monotonic_align as ma
 from aligner_b200 import _lib
 PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
 dev = torch.device("cuda")
-LPT = "--lpt" in sys.argv          # measured: no gain (profiles/r01_notes.md), the argsort costs 40-90 us
 rows = []
 for B in (256, 512, 1024, 2048, 4096, 8192):
     rng = np.random.default_rng(1234 + 5)
@@ -26,13 +25,9 @@ for B in (256, 512, 1024, 2048, 4096, 8192):
     for c in range(nchunk):
         xl = torch.from_numpy(t_x[c * chunk:(c + 1) * chunk]).to(dev); yl = torch.from_numpy(t_y[c * chunk:(c + 1) * chunk]).to(dev)
         ws = ma._workspace(dev, torch.cuda.current_stream().cuda_stream, chunk, tx, ty)
-        def launch():          # the argsort that builds the longest-first order is inside the timed region
-            order = None
-            if LPT:
-                order = torch.argsort(xl.to(torch.int64) * yl.to(torch.int64), descending=True, stable=True).to(torch.int32)
-            _lib.check(_lib.lib.alb200_mas_device_ordered(vals.data_ptr(), xl.data_ptr(), yl.data_ptr(), order.data_ptr() if LPT else None,
-                                                          out.data_ptr(), 4, 0x3F800000, 1, None, None,
-                                                          chunk, tx, ty, -1e9, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+        def launch():
+            _lib.check(_lib.lib.alb200_mas_device(vals.data_ptr(), xl.data_ptr(), yl.data_ptr(), out.data_ptr(), 4, 0x3F800000, 1, None, None,
+                                                  chunk, tx, ty, -1e9, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
         launch(); torch.cuda.synchronize()
         ts = []
         for _ in range(3):
@@ -43,7 +38,7 @@ for B in (256, 512, 1024, 2048, 4096, 8192):
         cells += cc; algo += 4 * cc + 4.0 * chunk * tx * ty
     ms = sum(times)
     r = {"B": B, "ms": ms, "cells_per_s": cells / (ms * 1e-3), "utt_per_s": B / (ms * 1e-3), "GBps": algo / (ms * 1e-3) / 1e9,
-         "frac_of_hbm_peak": algo / (ms * 1e-3) / 1e9 / PEAK, "order": "lpt" if LPT else "batch", "config": _lib.describe(chunk, tx, ty)}
+         "frac_of_hbm_peak": algo / (ms * 1e-3) / 1e9 / PEAK, "config": _lib.describe(chunk, tx, ty)}
     rows.append(r)
     print("B=%5d  %8.2f ms  %.3e cells/s  %9.0f utt/s  %7.1f GB/s  %.3f of %.0f GB/s   %s" % (B, ms, r["cells_per_s"], r["utt_per_s"], r["GBps"], r["frac_of_hbm_peak"], PEAK, r["config"]), flush=True)
     del vals, out; torch.cuda.empty_cache()

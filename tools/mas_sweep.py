@@ -19,10 +19,7 @@ PEAK = 6549.1
 
 def bench(b, tx, ty, force, ragged=False, reps=30, dense=True):
     dense = dense and os.environ.get("DENSE", "1") == "1"
-    if force:
-        os.environ["ALB200_FORCE"] = force
-    else:
-        os.environ.pop("ALB200_FORCE", None)
+    _lib.set_option("force", force)
     dev = torch.device("cuda")
     rng = np.random.default_rng(5)
     if ragged:
@@ -48,7 +45,7 @@ def bench(b, tx, ty, force, ragged=False, reps=30, dense=True):
         return {"error": str(e)}
 
     def launch(i):
-        _lib.check(_lib.lib.alb200_mas_device_ex(vals[i % nsets].data_ptr(), vd[1] | (_lib.LAYOUT_VITS if vits else 0), xl.data_ptr(), yl.data_ptr(), None, 0, 0, 0, 0, None,
+        _lib.check(_lib.lib.alb200_mas_device_ex(vals[i % nsets].data_ptr(), vd[1] | (_lib.LAYOUT_VITS if vits else 0), xl.data_ptr(), yl.data_ptr(), None, 0, 0, 0, 0,
                                                  outs[i % nsets].data_ptr() if dense else None, 4, 0x3F800000, 1, None, None, None,
                                                  b, tx, ty, -1e9, ws.data_ptr(), ws.numel(), stream))
     for i in range(3):

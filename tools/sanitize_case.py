@@ -5,6 +5,7 @@ import numpy as np, torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import aligner_b200.monotonic_align as ma
 import aligner_b200.neg_cent as nc
+from aligner_b200 import _lib
 rng = np.random.default_rng(0)
 CASES = [(None, 5, 150, 260, torch.float32), ("2,32,2,1,1", 5, 150, 260, torch.float32), ("3,16,2,0,0", 5, 150, 260, torch.float32),
          ("2,32,2,0,1,2", 3, 300, 420, torch.float32),        # cluster of 2 CTAs per utterance
@@ -12,14 +13,13 @@ CASES = [(None, 5, 150, 260, torch.float32), ("2,32,2,1,1", 5, 150, 260, torch.f
          (None, 4, 150, 264, torch.bfloat16), (None, 200, 70, 136, torch.float16),     # native half-precision scores: skewed/TMA and throughput forms
          (None, 200, 70, 133, torch.float32)]                 # throughput regime, unaligned rows
 for force, b, tx, ty, dt in CASES:
-    if force: os.environ["ALB200_FORCE"] = force
-    else: os.environ.pop("ALB200_FORCE", None)
+    _lib.set_option("force", force)
     v = torch.randn(b, tx, ty, device="cuda").to(dt)
     t_x = rng.integers(1, tx + 1, b).astype(np.int32); t_y = np.array([rng.integers(t_x[i], ty + 1) for i in range(b)], np.int32)
     out = ma.maximum_path_lengths(v, torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda(), return_durations=True, return_frame_tokens=True)
     torch.cuda.synchronize()
     assert int(out["durations"].sum()) == int(t_y.sum())
-os.environ.pop("ALB200_FORCE", None)
+_lib.set_option("force", None)
 z = torch.randn(2, 40, 300, device="cuda"); m = torch.randn(2, 40, 150, device="cuda"); lg = torch.rand(2, 40, 150, device="cuda") - 0.5
 s = nc.gaussian_neg_cent(z, m, lg); q = nc.ota_log_prob(torch.randn(2, 80, 300, device="cuda"), torch.randn(2, 80, 150, device="cuda"))
 torch.cuda.synchronize()
