@@ -25,6 +25,7 @@ SYMBOLS = (
     "alb200_mas_workspace_bytes", "alb200_mas_status", "alb200_mas_describe", "alb200_maximum_path_c",
     "alb200_last_transfer_bytes", "alb200_launch_count",
     "alb200_neg_cent_gaussian", "alb200_neg_cent_ota",
+    "alb200_neg_cent_workspace_bytes", "alb200_neg_cent_gaussian_ws", "alb200_neg_cent_ota_ws",
 )
 
 
@@ -68,6 +69,12 @@ def _load() -> ctypes.CDLL:
     lib.alb200_neg_cent_gaussian.restype = i32
     lib.alb200_neg_cent_ota.argtypes = [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]
     lib.alb200_neg_cent_ota.restype = i32
+    lib.alb200_neg_cent_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    lib.alb200_neg_cent_workspace_bytes.restype = sz
+    lib.alb200_neg_cent_gaussian_ws.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]
+    lib.alb200_neg_cent_gaussian_ws.restype = i32
+    lib.alb200_neg_cent_ota_ws.argtypes = [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp, sz, vp]
+    lib.alb200_neg_cent_ota_ws.restype = i32
     return lib
 
 
@@ -82,6 +89,11 @@ def check(rc: int) -> None:
 def set_option(name: str, value=None) -> None:
     """Tuning / test options (include/aligner_b200.h: alb200_set_option); value None restores the default."""
     check(lib.alb200_set_option(name.encode(), None if value is None else str(value).encode()))
+    for hook in _option_hooks:
+        hook()
+
+
+_option_hooks: list = []      # callables run after every option change (the Python layer drops its workspace-size memo)
 
 
 def describe(b: int, tx: int, ty: int, want_durations: bool = False) -> str:

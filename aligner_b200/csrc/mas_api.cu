@@ -31,6 +31,7 @@ static int set_opt_locked(const char* name, const char* value)
     else if (!strcmp(name, "dbg")) g_opts.dbg = unset ? 0 : atoi(value) != 0;
     else if (!strcmp(name, "nc_ffma")) g_opts.nc_ffma = unset ? 0 : atoi(value) != 0;
     else if (!strcmp(name, "nc_v1")) g_opts.nc_v1 = unset ? 0 : atoi(value) != 0;
+    else if (!strcmp(name, "nc_no_pdl")) g_opts.nc_no_pdl = unset ? 0 : atoi(value) != 0;
     else return -1;
     ++g_opts.gen;
     return 0;
@@ -41,7 +42,7 @@ static void opts_from_env()
     g_opts.latency_max_b = -1; g_opts.tmap_promo = -1;
     static const char* const names[][2] = { {"ALB200_FORCE", "force"}, {"ALB200_LATENCY_MAX_B", "latency_max_b"}, {"ALB200_TMAP_PROMO", "tmap_promo"},
         {"ALB200_NO_TAIL_BOX", "no_tail_box"}, {"ALB200_FORCE_UNALIGNED", "force_unaligned"}, {"ALB200_DBG", "dbg"}, {"ALB200_NC_FFMA", "nc_ffma"},
-        {"ALB200_NC_V1", "nc_v1"} };
+        {"ALB200_NC_V1", "nc_v1"}, {"ALB200_NC_NO_PDL", "nc_no_pdl"} };
     for (auto& n : names)
         if (const char* e = getenv(n[0])) set_opt_locked(n[1], e[0] ? e : "1");
 }
@@ -101,6 +102,9 @@ struct KEntry { int R, TF, skew, nwmax, minb; KernelFn fn; int vt; };     // vt:
 #define ALB_KC(R) { R, 32, 2, 4, 1, mas_kernel<R, 32, true, 4, 1, true> }      // skew code 2 = skewed + cluster hand-off
 #define ALB_KS8(R) { R, 32, 1, 8, 1, mas_kernel<R, 32, true, 8, 1> }
 static const KEntry g_kernels[] = {
+#ifdef ALB200_FEW_KERNELS          // A/B builds while tuning (build_lib.py --variant): the instances of the latency regime + one throughput instance
+    ALB_K(2, 32), ALB_K(4, 16), ALB_KS(1), ALB_KS(2), ALB_KS(3), ALB_KS8(1), ALB_KC(1), ALB_KC(2),
+#else
     ALB_K(1, 32),
     ALB_K(2, 32), ALB_K(2, 16),
     ALB_K(3, 32), ALB_K(3, 16),
@@ -125,6 +129,7 @@ static const KEntry g_kernels[] = {
     // VITS layout (scores and path stored [b, t_mel, t_text]): skewed/TMA form, fp32, skew code 3
     { 1, 32, 3, 4, 1, mas_kernel<1, 32, true, 4, 1, false, 0, true>, 0 }, { 2, 32, 3, 4, 1, mas_kernel<2, 32, true, 4, 1, false, 0, true>, 0 },
     { 3, 32, 3, 4, 1, mas_kernel<3, 32, true, 4, 1, false, 0, true>, 0 }, { 4, 32, 3, 4, 1, mas_kernel<4, 32, true, 4, 1, false, 0, true>, 0 },
+#endif
 };
 // Latency regime = one utterance per SM at a time: 255-register instances, skewed/TMA form, deepest ring, bits in shared
 // memory, and a persistent grid with the work cursor when the batch exceeds the SM count.  It obviously applies while
@@ -305,16 +310,21 @@ static int select_config(const DevInfo& di, int b, int tx, int ty, bool want_dur
 // loader fetches one box per tile (cp.async.bulk.tensor).  Encoding is host-side arithmetic; the last few are remembered.
 typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int values_tensor_map(const void* values, int vt, int vl, int b, int tx, int ty, int box_rows, int box_frames, CUtensorMap* out)
+TmapEncodeFn tmap_encode_fn()          // also used by neg_cent_v2.cu; nullptr when the driver lacks the entry point
 {
     static TmapEncodeFn enc = nullptr;
     if (!enc) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
-        ALB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-        if (!fn || q != cudaDriverEntryPointSuccess) return fail(ALB200_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver%s", "");
-        enc = reinterpret_cast<TmapEncodeFn>(fn);
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn && q == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<TmapEncodeFn>(fn);
     }
+    return enc;
+}
+static int values_tensor_map(const void* values, int vt, int vl, int b, int tx, int ty, int box_rows, int box_frames, CUtensorMap* out)
+{
+    TmapEncodeFn enc = tmap_encode_fn();
+    if (!enc) return fail(ALB200_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver%s", "");
     struct Key { const void* v; int b, tx, ty, br, bf, vt, vl; unsigned gen; };
     static thread_local Key keys[16];
     static thread_local CUtensorMap maps[16];

@@ -57,6 +57,9 @@ constexpr int kZeroChunk = 7168;   // bytes per zero-fill bulk store (56 x 128; 
 constexpr int kLanePad = 16;       // bytes of skew per lane inside a tile stage
 constexpr int kSkewLag = 1;        // frames lane l trails lane l-1 in the skewed form
 constexpr int kProgDone = 0x3fffffff;
+#ifndef ALB_SPEC_ADD
+#define ALB_SPEC_ADD 1
+#endif
 #ifndef ALB200_DBG_BUILD
 #define ALB200_DBG_BUILD 0
 #endif
@@ -410,7 +413,16 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
                 const float move = (r == 0) ? upv : S.old[r - 1];   // v_prev (core.pyx:29)
                 const bool take = move > stay;                      // core.c:19384
                 const float vr = SKEW ? vq[kk & 1][r] : ((k == 0) ? v[r].x : (k == 1) ? v[r].y : (k == 2) ? v[r].z : v[r].w);
-                float res = (take ? move : stay) + vr;              // core.pyx:30
+                float res;
+                if (ALB_SPEC_ADD && SKEW) {
+                    // latency regime (one warp per scheduler, chain-bound): both candidate sums are formed while the compare runs and
+                    // the select comes last -- the dependent chain per frame is {FADD | FSETP} -> FSEL instead of FSETP -> FSEL -> FADD.
+                    // Bit-identical: the selected operand meets the same single fp32 add (core.pyx:30).
+                    const float rs = stay + vr, rm = move + vr;
+                    res = take ? rm : rs;
+                } else {
+                    res = (take ? move : stay) + vr;                // core.pyx:30
+                }
                 if (DIAG) res = (dxy + r > kk) ? neg : res;         // rows above the diagonal stay at the sentinel
                 nv[r] = res;
                 if (take) hb[r] |= (1u << k);

@@ -259,17 +259,30 @@ using namespace albnc;
 
 extern "C" int alb200_neg_cent_gaussian_tc(const float*, const float*, const float*, float*, int, int, int, int, void*);
 extern "C" int alb200_neg_cent_ota_tc(const float*, const float*, const float*, const int32_t*, float*, float, int, int, int, int, void*);
+extern "C" int alb200_neg_cent_gaussian_v2(const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, void*);
+extern "C" int alb200_neg_cent_ota_v2(const float*, const float*, const float*, const int32_t*, float*, float, int, int, int, int, void*, size_t, void*);
+extern "C" size_t alb200_neg_cent_workspace_bytes(int mode, int b, int c, int tx, int ty);
 
+// Dispatch order (every path is CUDA; the later ones exist for shapes the earlier ones do not take and as cross-checks):
+//   1. neg_cent_v2.cu   tcgen05 fp16x3, TMA-fed, warp-specialised, persistent   (t_x <= 512, t_y % 4 == 0, a workspace)
+//   2. neg_cent_tc.cu   tcgen05 tf32x3, operands fetched with plain loads       (option "nc_v1"; OTA: t_x <= 512)
+//   3. the fp32 FFMA kernels above                                              (option "nc_ffma"; OTA with t_x > 512)
 extern "C" {
 
-int alb200_neg_cent_gaussian(const float* z, const float* m_p, const float* logs_p, float* out, int b, int c, int tx, int ty, void* stream)
+int alb200_neg_cent_gaussian_ws(const float* z, const float* m_p, const float* logs_p, float* out, int b, int c, int tx, int ty, void* workspace,
+                                size_t workspace_bytes, void* stream)
 {
     if (!z || !m_p || !logs_p || !out || b < 0 || c <= 0 || tx <= 0 || ty <= 0) return nc_fail(ALB200_E_INVALID, "neg_cent_gaussian: null pointer or bad shape");
     if (b == 0) return 0;
     if (b > 65535) return nc_fail(ALB200_E_UNSUPPORTED, "neg_cent_gaussian: batch > 65535");
-    // default: tensor cores (tcgen05, 3xTF32, fp32 accumulate in TMEM).  ALB200_NC_FFMA=1 selects the CUDA-core kernel below
-    // (kept as the fixed-order fp32 cross-check of the tensor-core path, tests/test_neg_cent_gpu.py).
-    if (!alb::opts().nc_ffma) return alb200_neg_cent_gaussian_tc(z, m_p, logs_p, out, b, c, tx, ty, stream);
+    const alb::Opts& o = alb::opts();
+    if (!o.nc_ffma) {
+        if (!o.nc_v1 && workspace) {
+            const int rc = alb200_neg_cent_gaussian_v2(z, m_p, logs_p, out, b, c, tx, ty, workspace, workspace_bytes, stream);
+            if (rc != ALB200_E_UNSUPPORTED) return rc;
+        }
+        return alb200_neg_cent_gaussian_tc(z, m_p, logs_p, out, b, c, tx, ty, stream);
+    }
     dim3 grid((ty + GBN - 1) / GBN, (tx + GBM - 1) / GBM, b);
     gaussian_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, m_p, logs_p, out, c, tx, ty);
     ++alb::g_launches;
@@ -278,15 +291,21 @@ int alb200_neg_cent_gaussian(const float* z, const float* m_p, const float* logs
     return 0;
 }
 
-int alb200_neg_cent_ota(const float* queries, const float* keys, const float* prior, const int32_t* x_lengths, float* out,
-                        float temperature, int b, int c, int tx, int ty, void* stream)
+int alb200_neg_cent_ota_ws(const float* queries, const float* keys, const float* prior, const int32_t* x_lengths, float* out,
+                           float temperature, int b, int c, int tx, int ty, void* workspace, size_t workspace_bytes, void* stream)
 {
     if (!queries || !keys || !out || b < 0 || c <= 0 || tx <= 0 || ty <= 0) return nc_fail(ALB200_E_INVALID, "neg_cent_ota: null pointer or bad shape");
     if (b == 0) return 0;
     if (b > 65535) return nc_fail(ALB200_E_UNSUPPORTED, "neg_cent_ota: batch > 65535");
-    // default: tensor cores; the log-softmax over the text axis is done on the accumulator in tensor memory, which holds
-    // 512 tokens.  Longer texts (and ALB200_NC_FFMA=1) take the CUDA-core kernel below.
-    if (tx <= 512 && !alb::opts().nc_ffma) return alb200_neg_cent_ota_tc(queries, keys, prior, x_lengths, out, temperature, b, c, tx, ty, stream);
+    const alb::Opts& o = alb::opts();
+    if (tx <= 512 && !o.nc_ffma) {
+        // the log-softmax over the text axis is done on the accumulator in tensor memory, which holds 512 tokens
+        if (!o.nc_v1 && workspace) {
+            const int rc = alb200_neg_cent_ota_v2(queries, keys, prior, x_lengths, out, temperature, b, c, tx, ty, workspace, workspace_bytes, stream);
+            if (rc != ALB200_E_UNSUPPORTED) return rc;
+        }
+        return alb200_neg_cent_ota_tc(queries, keys, prior, x_lengths, out, temperature, b, c, tx, ty, stream);
+    }
     size_t fixed = ((size_t)c * OBN + (size_t)c * OBX + OBN + 2 * 8 * OBN) * sizeof(float);
     size_t dbytes = (size_t)tx * (OBN + 1) * sizeof(float);
     int optin = 0, dev = 0;
@@ -305,6 +324,39 @@ int alb200_neg_cent_ota(const float* queries, const float* keys, const float* pr
     e = cudaGetLastError();
     if (e != cudaSuccess) return nc_fail(ALB200_E_CUDA, cudaGetErrorString(e));
     return 0;
+}
+
+// The entries without a workspace argument take the scratch of the TMA path from the stream-ordered allocator
+// (cudaMallocAsync / cudaFreeAsync on `stream`: no synchronisation, capturable into a CUDA graph).
+static int with_async_workspace(int mode, int b, int c, int tx, int ty, void* stream, void** ws, size_t* bytes)
+{
+    *ws = nullptr; *bytes = 0;
+    const alb::Opts& o = alb::opts();
+    if (o.nc_ffma || o.nc_v1 || b <= 0) return 0;
+    const size_t need = alb200_neg_cent_workspace_bytes(mode, b, c, tx, ty);
+    if (!need) return 0;
+    if (cudaMallocAsync(ws, need, (cudaStream_t)stream) != cudaSuccess) { cudaGetLastError(); *ws = nullptr; return 0; }   // fall through to the next path
+    *bytes = need;
+    return 0;
+}
+
+int alb200_neg_cent_gaussian(const float* z, const float* m_p, const float* logs_p, float* out, int b, int c, int tx, int ty, void* stream)
+{
+    void* ws; size_t bytes;
+    with_async_workspace(0, b, c > 0 ? c : 1, tx, ty, stream, &ws, &bytes);
+    const int rc = alb200_neg_cent_gaussian_ws(z, m_p, logs_p, out, b, c, tx, ty, ws, bytes, stream);
+    if (ws) cudaFreeAsync(ws, (cudaStream_t)stream);
+    return rc;
+}
+
+int alb200_neg_cent_ota(const float* queries, const float* keys, const float* prior, const int32_t* x_lengths, float* out,
+                        float temperature, int b, int c, int tx, int ty, void* stream)
+{
+    void* ws; size_t bytes;
+    with_async_workspace(1, b, c > 0 ? c : 1, tx, ty, stream, &ws, &bytes);
+    const int rc = alb200_neg_cent_ota_ws(queries, keys, prior, x_lengths, out, temperature, b, c, tx, ty, ws, bytes, stream);
+    if (ws) cudaFreeAsync(ws, (cudaStream_t)stream);
+    return rc;
 }
 
 }  // extern "C"

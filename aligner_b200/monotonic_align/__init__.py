@@ -34,6 +34,7 @@ _MASK_DTYPE = {
 
 _workspaces: dict = {}
 _ws_bytes: dict = {}
+_lib._option_hooks.append(_ws_bytes.clear)      # a forced kernel shape changes the scratch size
 
 
 def _workspace(device: torch.device, stream: int, b: int, tx: int, ty: int) -> torch.Tensor:

@@ -26,6 +26,15 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+def _scratch(mode: int, b: int, c: int, tx: int, ty: int, device: torch.device):
+    """Device scratch of the TMA / tcgen05 path (text-side operand staged once per utterance), from torch's caching
+    allocator -- stream-ordered like every other torch tensor, so it is safe under CUDA-graph capture too."""
+    need = int(_lib.lib.alb200_neg_cent_workspace_bytes(mode, b, c, tx, ty))
+    if not need:
+        return None, 0
+    return torch.empty(need, dtype=torch.uint8, device=device), need
+
+
 def gaussian_neg_cent(z: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor) -> torch.Tensor:
     """z [b,c,t_mel], m_p / logs_p [b,c,t_text]  ->  neg_cent [b,t_text,t_mel] fp32:
     sum_c log N(z[b,c,y]; m_p[b,c,x], exp(logs_p[b,c,x])^2)  (Glow-TTS logp1..4, VITS neg_cent1..4)."""
@@ -37,8 +46,10 @@ def gaussian_neg_cent(z: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor) 
     with torch.cuda.device(z.device):
         out = torch.empty((b, tx, ty), dtype=torch.float32, device=z.device)
         if b and tx and ty:
-            _lib.check(_lib.lib.alb200_neg_cent_gaussian(z.data_ptr(), m_p.data_ptr(), logs_p.data_ptr(), out.data_ptr(), b, c, tx, ty,
-                                                         torch.cuda.current_stream(z.device).cuda_stream))
+            ws, need = _scratch(0, b, c, tx, ty, z.device)
+            _lib.check(_lib.lib.alb200_neg_cent_gaussian_ws(z.data_ptr(), m_p.data_ptr(), logs_p.data_ptr(), out.data_ptr(), b, c, tx, ty,
+                                                            ws.data_ptr() if ws is not None else None, need,
+                                                            torch.cuda.current_stream(z.device).cuda_stream))
     return out
 
 
@@ -63,7 +74,9 @@ def ota_log_prob(queries: torch.Tensor, keys: torch.Tensor, temperature: float =
     with torch.cuda.device(q.device):
         out = torch.empty((b, tx, ty), dtype=torch.float32, device=q.device)
         if b and tx and ty:
-            _lib.check(_lib.lib.alb200_neg_cent_ota(q.data_ptr(), k.data_ptr(), pr.data_ptr() if pr is not None else None,
-                                                    xl.data_ptr() if xl is not None else None, out.data_ptr(), float(temperature),
-                                                    b, c, tx, ty, torch.cuda.current_stream(q.device).cuda_stream))
+            ws, need = _scratch(1, b, c, tx, ty, q.device)
+            _lib.check(_lib.lib.alb200_neg_cent_ota_ws(q.data_ptr(), k.data_ptr(), pr.data_ptr() if pr is not None else None,
+                                                       xl.data_ptr() if xl is not None else None, out.data_ptr(), float(temperature),
+                                                       b, c, tx, ty, ws.data_ptr() if ws is not None else None, need,
+                                                       torch.cuda.current_stream(q.device).cuda_stream))
     return out

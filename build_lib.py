@@ -19,7 +19,7 @@ PKG = Path(__file__).resolve().parent / "aligner_b200"
 CSRC = PKG / "csrc"
 LIB = PKG / "libaligner_b200.so"
 OBJ = CSRC / "_obj"
-SOURCES = ["mas_api.cu", "neg_cent.cu", "neg_cent_tc.cu"]
+SOURCES = ["mas_api.cu", "neg_cent.cu", "neg_cent_tc.cu", "neg_cent_v2.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -66,13 +66,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
-def build_dbg() -> Path:
-    """Developer variant with the per-warp clock64 stamps compiled in (tools/dbg_timing.py): libaligner_b200_dbg.so."""
+def build_variant(name: str, defines=()) -> Path:
+    """Developer variants (never shipped, never loaded unless ALB200_LIB points at them): libaligner_b200_<name>.so.
+    `dbg` = per-warp clock64 stamps compiled in (tools/dbg_timing.py, tools/nc_timeline.py); others are A/B builds
+    (python build_lib.py --variant nospec -DALB_SPEC_ADD=0 -DALB200_FEW_KERNELS=1)."""
     srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
     OBJ.mkdir(exist_ok=True)
     with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
-        objs = list(ex.map(lambda s: _compile(s, False, ("-DALB200_DBG_BUILD=1",), "_dbg"), srcs))
-    out = PKG / "libaligner_b200_dbg.so"
+        objs = list(ex.map(lambda s: _compile(s, False, tuple(defines), "_" + name), srcs))
+    out = PKG / ("libaligner_b200_%s.so" % name)
     proc = subprocess.run([NVCC, "-shared", "-o", str(out), *map(str, objs), "-lcudart"], capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (proc.stdout, proc.stderr))
@@ -81,7 +83,11 @@ def build_dbg() -> Path:
 
 if __name__ == "__main__":
     if "--dbg" in sys.argv:
-        print(build_dbg())
+        print(build_variant("dbg", ["-DALB200_DBG_BUILD=1"]))
+        sys.exit(0)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")]))
         sys.exit(0)
     out = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(out)

@@ -160,7 +160,8 @@ void alb200_last_transfer_bytes(uint64_t *h2d, uint64_t *d2h);
  * tree, README.md:9-25); they implement the published formulas of the projects it links to
  * and produce the layout the reference API documents: [b, t_text, t_mel], t_mel contiguous
  * (monotonic_align/__init__.py:8-9).  fp32 in, fp32 out.  Default path: 5th-generation tensor cores (tcgen05) with every
- * operand split into two half-width parts (three products, fp32 accumulation in tensor memory) -- within 1e-5 of the fp64
+ * operand split into two fp16 parts after an exact power-of-two scaling (three products, fp32 accumulation in tensor
+ * memory; a tile whose mel-side values leave the fp16 range is recomputed in plain fp32) -- within 1e-5 of the fp64
  * value relative to the largest |score| of the utterance; the Gaussian score is formed as the contraction plus a per-token
  * term, the OTA distance as |q|^2 + |k|^2 - 2 q.k.  Option "nc_ffma" selects fixed-order fp32 FFMA kernels instead.
  *
@@ -179,6 +180,18 @@ int alb200_neg_cent_gaussian(const float *z, const float *m_p, const float *logs
 int alb200_neg_cent_ota(const float *queries, const float *keys, const float *prior,
                         const int32_t *x_lengths, float *out, float temperature,
                         int b, int c, int tx, int ty, void *stream);
+
+/* The same two score matrices with caller-provided device scratch (what the Python layer calls: the scratch comes from the
+ * framework's caching allocator).  The default tensor-core path stages the text-side operand of every utterance once, as
+ * scaled fp16 hi / lo parts, in `workspace`; alb200_neg_cent_workspace_bytes(mode, ...) gives its size (mode 0 = Gaussian,
+ * 1 = OTA; 0 = this shape takes a path that needs no scratch).  workspace must be 256-byte aligned; NULL selects the
+ * paths without scratch.  The entries above allocate the same scratch with cudaMallocAsync / cudaFreeAsync on `stream`. */
+size_t alb200_neg_cent_workspace_bytes(int mode, int b, int c, int tx, int ty);
+int alb200_neg_cent_gaussian_ws(const float *z, const float *m_p, const float *logs_p, float *out,
+                                int b, int c, int tx, int ty, void *workspace, size_t workspace_bytes, void *stream);
+int alb200_neg_cent_ota_ws(const float *queries, const float *keys, const float *prior,
+                           const int32_t *x_lengths, float *out, float temperature,
+                           int b, int c, int tx, int ty, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Number of kernels this library has launched on this thread since load. */
 uint64_t alb200_launch_count(void);

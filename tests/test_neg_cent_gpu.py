@@ -81,6 +81,88 @@ def test_tensor_core_and_cuda_core_paths_agree(nc, b, c, tx, ty):
     assert (tc_o - ff_o).abs().max() <= TOL * ff_o.abs().max()
 
 
+def test_three_generations_agree(nc):
+    """fp16x3 / TMA (default), tf32x3 (option nc_v1) and FFMA (option nc_ffma): three independent implementations."""
+    from aligner_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(17)
+    b, c, tx, ty = 3, 192, 200, 1000
+    z = torch.randn(b, c, ty, generator=g, device="cuda")
+    m = torch.randn(b, c, tx, generator=g, device="cuda")
+    logs = torch.rand(b, c, tx, generator=g, device="cuda") * 1.5 - 1.0
+    q, k = torch.randn(b, 80, ty, generator=g, device="cuda"), torch.randn(b, 80, tx, generator=g, device="cuda")
+    n0 = _lib.launch_count()
+    g2, o2 = nc.gaussian_neg_cent(z, m, logs), nc.ota_log_prob(q, k)
+    assert _lib.launch_count() - n0 == 4                     # prep + main kernel, twice: the TMA path really ran
+    outs = {}
+    for opt in ("nc_v1", "nc_ffma"):
+        _lib.set_option(opt, "1")
+        try:
+            n0 = _lib.launch_count()
+            outs[opt] = (nc.gaussian_neg_cent(z, m, logs), nc.ota_log_prob(q, k))
+            assert _lib.launch_count() - n0 == 2
+        finally:
+            _lib.set_option(opt, None)
+    for opt, (gg, oo) in outs.items():
+        assert (g2 - gg).abs().max() <= TOL * gg.abs().max(), opt
+        assert (o2 - oo).abs().max() <= TOL * oo.abs().max(), opt
+
+
+@pytest.mark.parametrize("scale,expect_exact_path", [(1.0, False), (3000.0, True)])
+def test_mel_side_outside_fp16_range_is_recomputed_exactly(nc, scale, expect_exact_path):
+    """The mel side uses fixed power-of-two factors that are exact for |z| < 500 (|q| < 1000); a tile that sees more (or a
+    non-finite value) is recomputed by its own CTA in plain fp32 -- slow, exact, never silent."""
+    g = torch.Generator(device="cuda").manual_seed(23)
+    b, c, tx, ty = 2, 64, 90, 520
+    z = torch.randn(b, c, ty, generator=g, device="cuda")
+    z[:, :, 130:140] *= scale                               # only the second mel tile of every utterance is affected
+    m = torch.randn(b, c, tx, generator=g, device="cuda")
+    logs = torch.rand(b, c, tx, generator=g, device="cuda") * 1.5 - 1.0
+    got = nc.gaussian_neg_cent(z, m, logs).cpu().numpy()
+    want = nc_oracle.gaussian_neg_cent(z.cpu().numpy(), m.cpu().numpy(), logs.cpu().numpy())
+    for i in range(b):                                      # per mel tile: the huge frames must not hide errors elsewhere
+        for y0 in range(0, ty, 128):
+            assert rel_err(got[i, :, y0:y0 + 128], want[i, :, y0:y0 + 128]) <= TOL, (i, y0)
+    q = torch.randn(b, 80, ty, generator=g, device="cuda")
+    q[:, :, 300:310] *= scale
+    k = torch.randn(b, 80, tx, generator=g, device="cuda")
+    got = nc.ota_log_prob(q, k, 0.0005).cpu().numpy()
+    if not expect_exact_path:
+        want = nc_oracle.ota_log_prob(q.cpu().numpy(), k.cpu().numpy(), 0.0005)
+    else:
+        # |q| ~ 1e4: the sum of squared differences is ~1e10 and no fp32 evaluation reaches 1e-5 of fp64 any more; the exact path
+        # must agree with the fixed-order fp32 FFMA kernel (same expression, same order) instead
+        from aligner_b200 import _lib
+        _lib.set_option("nc_ffma", "1")
+        try:
+            want = nc.ota_log_prob(q, k, 0.0005).cpu().numpy().astype(np.float64)
+        finally:
+            _lib.set_option("nc_ffma", None)
+    for y0 in range(0, ty, 128):
+        assert rel_err(got[:, :, y0:y0 + 128], want[:, :, y0:y0 + 128]) <= TOL, y0
+    if expect_exact_path:                                   # NaN in, NaN out -- for the frames that hold it, not for the rest
+        z[0, 3, 7] = float("nan")
+        got = nc.gaussian_neg_cent(z, m, logs)
+        assert torch.isnan(got[0, :, 7]).all() and torch.isfinite(got[0, :, 8]).all() and torch.isfinite(got[1]).all()
+
+
+def test_c_entry_without_workspace(nc):
+    """alb200_neg_cent_gaussian / _ota (no scratch argument) take the scratch from the stream-ordered allocator."""
+    from aligner_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(29)
+    b, c, tx, ty = 2, 40, 70, 260
+    z = torch.randn(b, c, ty, generator=g, device="cuda")
+    m = torch.randn(b, c, tx, generator=g, device="cuda")
+    logs = torch.rand(b, c, tx, generator=g, device="cuda") - 0.5
+    out = torch.empty(b, tx, ty, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    n0 = _lib.launch_count()
+    _lib.check(_lib.lib.alb200_neg_cent_gaussian(z.data_ptr(), m.data_ptr(), logs.data_ptr(), out.data_ptr(), b, c, tx, ty, st))
+    assert _lib.launch_count() - n0 == 2
+    assert torch.equal(out, nc.gaussian_neg_cent(z, m, logs))
+    _lib.check(_lib.lib.alb200_neg_cent_ota(z.data_ptr(), m.data_ptr(), None, None, out.data_ptr(), 0.0005, b, c, tx, ty, st))
+    assert torch.equal(out, nc.ota_log_prob(z, m, 0.0005))
+
+
 def _agreement(ma, score_gpu, score_ref64, t_x, t_y):
     ref32 = np.ascontiguousarray(score_ref64.astype(np.float32))
     want = np.zeros(ref32.shape, np.int32)
