@@ -377,6 +377,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                         for (int prod = 0; prod < 3; ++prod) {
                             const uint32_t sa = (prod == 1) ? sA_lo : sA_hi;         // hi*hi, lo*hi, hi*lo
                             const uint32_t sb = (prod == 2) ? sB_lo : sB_hi;
+#ifndef NC_NO_LOOKAHEAD
                             if (prod == 2 && !(pass == p.npass - 1 && ch == p.nchunks - 1)) {
                                 // the tensor pipe still has this chunk's first two products queued: the barrier round trips of the
                                 // NEXT chunk (same tile) hide behind them instead of opening a gap between the chunks
@@ -385,6 +386,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                                 mbar_wait(bar_b_full + 8 * s2, ph2);
                                 ready = true;
                             }
+#endif
                             for (int ks = 0; ks < nk; ++ks)                          // 16 fp16 = 32 bytes along the swizzled row
                                 mma_f16(dcol, make_desc(sa + ks * 32), make_desc(sb + ks * 32), idesc, (ch | prod | ks) ? 1u : 0u);
                         }
@@ -417,10 +419,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                 const uint32_t src = raw0 + rs * RAW_BYTES + (uint32_t)(16 * half) * (BM * 4) + (uint32_t)row * 4u;
 #pragma unroll
                 for (int q = 0; q < 16; ++q) v[q] = lds32(src + q * (BM * 4));
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_raw_empty + 8 * rs);       // this warp has read its part of the box
 #pragma unroll
                 for (int q = 0; q < 16; ++q) bad = bad || !(fabsf(v[q]) < (MODE == 0 ? kZLimit : kQLimit));   // also catches NaN
+                // The stage may be handed back only when the loads have RETURNED, not merely been issued: the barrier arrival is not
+                // ordered behind outstanding shared-memory loads, and under a saturated shared-memory pipe (the tensor core reads its
+                // operands there) a load can still be queued when the next TMA box lands -- seen as sporadic stale frames with a
+                // one-stage ring.  The range check above consumes every loaded value, the warp issues in order, and the arrival takes
+                // the check's result as an operand so that the compiler cannot sink the check below it.
+                __syncwarp();
+                if (lane == 0) asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.shared::cta.b64 t, [%0];\n\t}" ::"r"(bar_raw_empty + 8 * rs), "r"((int)bad) : "memory");
                 if (MODE == 0) {
                     // 16 channels -> 32 k = four 16-byte pieces (4 channels each) of hi and of lo; piece index 4*half + j
 #pragma unroll
@@ -509,6 +516,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
             const uint32_t tcol = tlane + slot * 256u;
             const bool slow = ovf[it & 7] != 0;              // the mel side of this tile left the fp16 range: exact fp32 path below
             const int ngroups = p.NT >> 4;
+#ifdef NC_CHECK_TMEM
+            {   // developer check: the accumulator must not change while the epilogue owns it
+                uint32_t h1 = 0, h2 = 0;
+                for (int g = 0; g < ngroups; ++g) { uint32_t r[16]; tmem_ld16(tcol + (uint32_t)(16 * g), r); for (int j = 0; j < 16; ++j) h1 = h1 * 31u + r[j]; }
+                for (int spin = 0; spin < 2000; ++spin) asm volatile("nanosleep.u32 20;");
+                for (int g = 0; g < ngroups; ++g) { uint32_t r[16]; tmem_ld16(tcol + (uint32_t)(16 * g), r); for (int j = 0; j < 16; ++j) h2 = h2 * 31u + r[j]; }
+                if (h1 != h2) { printf("TMEM changed under the epilogue: block %d item %d row %d\n", (int)blockIdx.x, item, row); }
+            }
+#endif
             // Full groups of 16 tokens take a branch-free path (one FFMA [+ one add] and one 128-byte-per-warp store per cell); the
             // ragged last group takes the predicated one.
 #define NC_LOAD_TERMS(g)                                                                                                      \
