@@ -14,6 +14,7 @@ struct Opts {
     int dbg;               // 1: per-warp clock64 stamps on stderr (needs a -DALB200_DBG_BUILD=1 library)
     int nc_ffma;           // 1: CUDA-core score kernels (cross-check of the tensor-core path)
     int nc_v1;             // 1: first-generation tcgen05 score kernels (operands fetched with plain loads)
+    int fused_seq;         // fused score + search entry: 1 = always back to back, 2 = pipelined whenever possible (default: by batch size)
     int nc_no_pdl;         // 1: the score kernel waits for the whole prep kernel (no programmatic dependent launch)
     unsigned gen;
 };

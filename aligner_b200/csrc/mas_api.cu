@@ -28,10 +28,11 @@ static int set_opt_locked(const char* name, const char* value)
     else if (!strcmp(name, "tmap_promo")) g_opts.tmap_promo = unset ? -1 : atoi(value);
     else if (!strcmp(name, "no_tail_box")) g_opts.no_tail_box = unset ? 0 : atoi(value) != 0;
     else if (!strcmp(name, "force_unaligned")) g_opts.force_unaligned = unset ? 0 : atoi(value) != 0;
-    else if (!strcmp(name, "dbg")) g_opts.dbg = unset ? 0 : atoi(value) != 0;
+    else if (!strcmp(name, "dbg")) g_opts.dbg = unset ? 0 : atoi(value);
     else if (!strcmp(name, "nc_ffma")) g_opts.nc_ffma = unset ? 0 : atoi(value) != 0;
     else if (!strcmp(name, "nc_v1")) g_opts.nc_v1 = unset ? 0 : atoi(value) != 0;
     else if (!strcmp(name, "nc_no_pdl")) g_opts.nc_no_pdl = unset ? 0 : atoi(value) != 0;
+    else if (!strcmp(name, "fused_seq")) g_opts.fused_seq = unset ? 0 : atoi(value);
     else return -1;
     ++g_opts.gen;
     return 0;
@@ -42,7 +43,7 @@ static void opts_from_env()
     g_opts.latency_max_b = -1; g_opts.tmap_promo = -1;
     static const char* const names[][2] = { {"ALB200_FORCE", "force"}, {"ALB200_LATENCY_MAX_B", "latency_max_b"}, {"ALB200_TMAP_PROMO", "tmap_promo"},
         {"ALB200_NO_TAIL_BOX", "no_tail_box"}, {"ALB200_FORCE_UNALIGNED", "force_unaligned"}, {"ALB200_DBG", "dbg"}, {"ALB200_NC_FFMA", "nc_ffma"},
-        {"ALB200_NC_V1", "nc_v1"}, {"ALB200_NC_NO_PDL", "nc_no_pdl"} };
+        {"ALB200_NC_V1", "nc_v1"}, {"ALB200_NC_NO_PDL", "nc_no_pdl"}, {"ALB200_FUSED_SEQ", "fused_seq"} };
     for (auto& n : names)
         if (const char* e = getenv(n[0])) set_opt_locked(n[1], e[0] ? e : "1");
 }
@@ -363,7 +364,8 @@ static size_t ws_bytes_for(const Config& c)
 static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_ys, const void* mask, int mask_dtype,
                       int64_t msb, int64_t msx, int64_t msy, void* paths, int esize, uint64_t one, int zero_fill,
                       int32_t* frame_tok, int32_t* durations, int32_t* lens_out, int b, int tx, int ty, float neg,
-                      void* workspace, size_t workspace_bytes, cudaStream_t stream, int vt = 0, int vl = 0)
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream, int vt = 0, int vl = 0,
+                      const int* tile_ready = nullptr, int ready_epoch = 0, int ready_tiles = 0)
 {
     if (!values || b < 0 || tx <= 0 || ty <= 0) return fail(ALB200_E_INVALID, "null values or non-positive shape%s", "");
     if (!mask && (!t_xs || !t_ys)) return fail(ALB200_E_INVALID, "need lengths or a mask%s", "");
@@ -418,8 +420,9 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
         }
     }
     p.neg = neg;
+    p.tile_ready = tile_ready; p.ready_epoch = ready_epoch; p.ready_tiles = ready_tiles;
     static long long* d_dbg = nullptr;
-    const bool dbg = kDbgBuild && opts().dbg;
+    const bool dbg = kDbgBuild && opts().dbg == 1;
     const size_t dbg_n = (size_t)c.grid * ((2 * kMaxWarps + 2) * 2 + kMaxWarps * 8);
     if (dbg) {   // developer aid: per-warp clock64 stamps of the first item of every CTA, printed to stderr
         if (d_dbg) cudaFree(d_dbg);
@@ -428,14 +431,25 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
         p.dbg = d_dbg;
     }
     void* args[] = { &p, &tmap, &tmap_tail };
-    if (c.nc > 1) {
+    if (c.nc > 1 || tile_ready != nullptr) {
         cudaLaunchConfig_t lc;
         memset(&lc, 0, sizeof(lc));
         lc.gridDim = dim3(c.grid); lc.blockDim = dim3(2 * c.NW * 32); lc.dynamicSmemBytes = c.smem; lc.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = c.nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        lc.attrs = at; lc.numAttrs = 1;
+        cudaLaunchAttribute at[2];
+        int na = 0;
+        if (c.nc > 1) {
+            at[na].id = cudaLaunchAttributeClusterDimension;
+            at[na].val.clusterDim.x = c.nc; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        if (tile_ready != nullptr) {
+            // pipelined with the score kernel launched just before on this stream: start beside it (it signals at its start and
+            // has left SMs free); the loader warps poll tile_ready, nothing here waits for that kernel as a whole
+            at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        lc.attrs = at; lc.numAttrs = na;
         ALB_CUDA(cudaLaunchKernelExC(&lc, (const void*)c.fn, args));
     } else {
         ALB_CUDA(cudaLaunchKernel((const void*)c.fn, dim3(c.grid), dim3(2 * c.NW * 32), args, c.smem, stream));
@@ -590,6 +604,79 @@ int alb200_mas_describe(int b, int tx, int ty, int want_durations, char* buf, si
         snprintf(buf, buf_bytes, "rows_per_lane=%d tile_frames=%d warps=%d stages=%d bits=%s form=%s smem=%u grid=%d ctas_per_sm=%d cluster=%d",
                  c.R, c.TF, c.NW, c.NS, c.bits_smem ? "smem" : "global", c.skew ? "skewed" : "lockstep", c.smem, c.grid, c.occ, c.nc);
     return 0;
+}
+
+// ---- fused score + search, pipelined form
+extern "C" size_t alb200_neg_cent_workspace_bytes(int mode, int b, int c, int tx, int ty);
+extern "C" int alb200_neg_cent_gaussian_ws(const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, void*);
+extern "C" int alb200_neg_cent_gaussian_v2_pipelined(const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, void*, int*, int, int);
+
+size_t alb200_fused_workspace_bytes(int b, int c, int tx, int ty)
+{
+    const size_t nc = alb200_neg_cent_workspace_bytes(0, b, c, tx, ty);
+    const size_t flags = ((size_t)b * ((ty + 127) / 128) * 4 + 1024 + 255) & ~(size_t)255;     // + slack for the developer time stamps
+    return ((nc + 255) & ~(size_t)255) + flags + alb200_mas_workspace_bytes(b, tx, ty);
+}
+
+int alb200_gaussian_mas_fused(const float* z, const float* m_p, const float* logs_p, float* neg_cent, const int32_t* t_xs, const int32_t* t_ys,
+                              const void* mask, int mask_dtype, int64_t msb, int64_t msx, int64_t msy, void* paths, int path_elem_size,
+                              uint64_t path_one, int zero_fill, int32_t* frame_tok, int32_t* durations, int b, int c, int tx, int ty,
+                              float max_neg_val, void* workspace, size_t workspace_bytes, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!z || !m_p || !logs_p || !neg_cent || !workspace || b < 0 || c <= 0 || tx <= 0 || ty <= 0)
+        return fail(ALB200_E_INVALID, "null pointer or non-positive shape%s", "");
+    if (b == 0) return 0;
+    if (workspace_bytes < alb200_fused_workspace_bytes(b, c, tx, ty)) return fail(ALB200_E_INVALID, "workspace too small (alb200_fused_workspace_bytes)%s", "");
+    const size_t nc_bytes = (alb200_neg_cent_workspace_bytes(0, b, c, tx, ty) + 255) & ~(size_t)255;
+    const int n_mt = (ty + 127) / 128;
+    const size_t flag_bytes = ((size_t)b * n_mt * 4 + 1024 + 255) & ~(size_t)255;
+    char* ws = reinterpret_cast<char*>(workspace);
+    int* flags = reinterpret_cast<int*>(ws + nc_bytes);
+    void* mas_ws = ws + nc_bytes + flag_bytes;
+    const size_t mas_ws_bytes = workspace_bytes - nc_bytes - flag_bytes;
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    // Pipelined when the search (one CTA or cluster per utterance) needs at most a third of the SMs: the score kernel runs on the
+    // others in tile-major order and publishes every 128-frame tile; the search is launched programmatically dependent, starts
+    // beside it and its loader warps wait per tile, so a tile is read out of L2 while later ones are still being computed.
+    // Measured (profiles/r02_notes.md): 32 x 300 x 1500 145 -> 117 us.  With more utterances the SMs taken away from the score
+    // kernel cost as much as the overlap gains (64 x 200 x 1000: 94 vs 93 us), and a batch that fills the machine is
+    // bandwidth-bound with nothing to overlap: those run the two kernels back to back.
+    Config cfg;
+    const bool aligned = (reinterpret_cast<uintptr_t>(neg_cent) & 15) == 0 && ((int64_t)ty * 4) % 16 == 0 && !opts().force_unaligned;
+    rc = select_config(di, b, tx, ty, durations != nullptr, aligned, &cfg, 0, 0);
+    if (rc) return rc;
+    const int free_sms = di.sms - cfg.grid;
+    const int fmode = opts().fused_seq;                       // tuning: 1 = always back to back, 2 = pipelined whenever possible
+    const bool can_pipe = nc_bytes > 0 && is_latency(di, b, tx, ty, aligned, 0) && cfg.grid <= di.sms && free_sms >= 32 && !opts().nc_ffma && !opts().nc_v1;
+    const bool pipelined = can_pipe && fmode != 1 && (fmode == 2 || cfg.grid * 3 <= di.sms);
+    if (pipelined) {
+        ALB_CUDA(cudaMemsetAsync(flags, 0, (size_t)b * n_mt * 4, stream));
+        if (kDbgBuild && opts().dbg == 2) {      // developer aid: global-timer stamps of both kernels (see the kernels)
+            unsigned long long init[4] = { ~0ull, 0ull, ~0ull, 0ull };
+            ALB_CUDA(cudaMemcpyAsync(flags + (size_t)b * n_mt + 64, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+        }
+        rc = alb200_neg_cent_gaussian_v2_pipelined(z, m_p, logs_p, neg_cent, b, c, tx, ty, ws, nc_bytes, stream, flags, 1, free_sms);
+        if (rc == 0) {
+            rc = launch_mas(neg_cent, t_xs, t_ys, mask, mask_dtype, msb, msx, msy, paths, path_elem_size, path_one, zero_fill, frame_tok, durations,
+                            nullptr, b, tx, ty, max_neg_val, mas_ws, mas_ws_bytes, stream, 0, 0, flags, 1, n_mt);
+            if (kDbgBuild && opts().dbg == 2 && rc == 0) {
+                unsigned long long h[4];
+                cudaStreamSynchronize(stream);
+                cudaMemcpy(h, flags + (size_t)b * n_mt + 64, sizeof(h), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[fused dbg] score kernel %.1f us (start 0), search starts at %.1f us, ends at %.1f us\n", (h[1] - h[0]) * 1e-3,
+                        ((double)h[2] - (double)h[0]) * 1e-3, ((double)h[3] - (double)h[0]) * 1e-3);
+            }
+            return rc;
+        }
+        if (rc != ALB200_E_UNSUPPORTED) return rc;
+    }
+    rc = alb200_neg_cent_gaussian_ws(z, m_p, logs_p, neg_cent, b, c, tx, ty, nc_bytes ? ws : nullptr, nc_bytes, stream);
+    if (rc) return rc;
+    return launch_mas(neg_cent, t_xs, t_ys, mask, mask_dtype, msb, msx, msy, paths, path_elem_size, path_one, zero_fill, frame_tok, durations,
+                      nullptr, b, tx, ty, max_neg_val, mas_ws, mas_ws_bytes, stream);
 }
 
 int alb200_mas_status(void* workspace, void* stream)

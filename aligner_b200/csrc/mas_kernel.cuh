@@ -85,6 +85,10 @@ struct MasParams {
     WsHeader* ws;
     uint32_t* bits_ws;          // global direction-bit slots (nullptr when bits are in smem)
     long long* dbg;             // optional [grid][2*kMaxWarps+2][2] clock64 stamps (ALB200_DBG)
+    // Pipelined with the score kernel (alb200_gaussian_mas_fused): `values` is being written by a kernel running beside this one;
+    // tile_ready[item * ready_tiles + k] == ready_epoch once frames [128 k, 128 k + 128) of every token row of `item` are in global memory.
+    const int* tile_ready;
+    int ready_epoch, ready_tiles;
     uint64_t one;
     int64_t bits_slot_words;
     int B, Tx, Ty;
@@ -264,6 +268,19 @@ __device__ __forceinline__ int wait_flag_ge(uint32_t a, int need, int seen) {
 __device__ __forceinline__ void wait_flag_le(uint32_t a, int need) {
     uint32_t n = 0;
     while (ld_flag(a) > need) spin_guard(n);
+}
+
+// Waits until producer tiles <= need of this utterance are published (see MasParams::tile_ready).  Every lane polls the same word
+// (one broadcast transaction); the acquire orders this lane's later loads, the proxy fence the TMA loads it issues, behind the
+// producer's stores.  Bounded like every other wait in this file.
+__device__ __forceinline__ void wait_tiles_ready(const int* flags, int epoch, int& known, int need) {
+    uint32_t n = 0;
+    while (known < need) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + known + 1) : "memory");
+        if (v == epoch) ++known; else { __nanosleep(64); spin_guard(n); }
+    }
+    asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ mask -> length
@@ -665,6 +682,10 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     fence_proxy_async_smem();
     __syncthreads();
 
+    if (kDbgBuild && p.tile_ready != nullptr && tid == 0) {   // developer aid: when did the pipelined search start / reach its first wait
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMin(reinterpret_cast<unsigned long long*>(const_cast<int*>(p.tile_ready) + (int64_t)p.B * p.ready_tiles + 64) + 2, gt);
+    }
     uint32_t stage = 0, phase = 0;          // ring cursor of this warp (consumer side for compute, producer side for loaders)
     const int64_t item_elems = (int64_t)p.Tx * p.Ty;
     const int Ty = p.Ty;
@@ -775,9 +796,15 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 const int64_t my_chunks = (nchunks > gw) ? (nchunks - gw + nact - 1) / nact : 0;
                 const int zq = (int)((my_chunks + my_tiles - 1) / (my_tiles > 0 ? my_tiles : 1));
                 long long l_e = 0, l_c = 0, l_z = 0, l0 = 0, l1 = 0, l2 = 0;
+                int known_ready = -1;                               // highest producer tile known to be published (pipelined mode)
                 for (int t = t_s; t < t_e; ++t) {
                     if (dbg_on) l0 = clock64();
                     mbar_wait(empty0 + 8 * stage, phase ^ 1u);      // the compute lanes have released this stage
+                    if (p.tile_ready != nullptr) {                 // scores still being produced: wait for the frames of this tile
+                        int need = (t * TF + TF - 1) >> 7;
+                        need = need < p.ready_tiles ? need : p.ready_tiles - 1;
+                        if (known_ready < need) wait_tiles_ready(p.tile_ready + (int64_t)item * p.ready_tiles, p.ready_epoch, known_ready, need);
+                    }
                     if (dbg_on) l1 = clock64();
                     const uint32_t st = ring_a + stage * L.stage_bytes;
                     if (SKEW) {
@@ -1008,6 +1035,10 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         item = misc[0];
     }
 
+    if (kDbgBuild && p.tile_ready != nullptr && tid == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMax(reinterpret_cast<unsigned long long*>(const_cast<int*>(p.tile_ready) + (int64_t)p.B * p.ready_tiles + 64) + 3, gt);
+    }
     if (NC == 1 && p.B > (int)gridDim.x && tid == 0) {
         const int d = atomicAdd(&p.ws->done, 1);
         if (d == (int)gridDim.x - 1) {      // last CTA out re-arms the counters for the next launch

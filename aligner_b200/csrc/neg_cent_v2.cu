@@ -254,6 +254,9 @@ constexpr int kDbgSlots = 64;                 // events kept per role
 
 struct V2Params {
     long long* dbg;
+    int* ready;                // pipelined with the search: ready[b * n_mtiles + mel tile] = epoch once the tile is in global memory
+    int epoch;
+    int tile_major;            // work order: all utterances' mel tile 0, then tile 1, ... (what a concurrent search consumes first)
     const float* a_src;        // raw mel side: z / queries [b, C, Ty]   (slow exact path only; the fast path reads it through TMA)
     const float* b_src0;       // raw text side: m_p / keys [b, C, Tx]    (slow exact path only)
     const float* b_src1;       // logs_p (gaussian)
@@ -271,6 +274,11 @@ struct V2Params {
     uint32_t off_a, off_b, off_aux, b_stage_bytes;   // raw ring at offset 0
 };
 
+__device__ __forceinline__ void item_to_tile(const V2Params& p, int item, int& b, int& mt) {
+    if (p.tile_major) { mt = item / p.B; b = item - mt * p.B; }
+    else { b = item / p.n_mtiles; mt = item - b * p.n_mtiles; }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, const __grid_constant__ CUtensorMap map_a,
                                                             const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo)
@@ -287,6 +295,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
     const int SR = p.sr;
 
     if ((base & 1023u) != 0u) __trap();                      // the swizzle atoms need 1024-byte alignment
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a search launched behind us may start beside us (it polls p.ready)
+    if (kDbg && p.ready != nullptr && tid == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMin(reinterpret_cast<unsigned long long*>(p.ready + (size_t)p.B * p.n_mtiles + 64) + 0, gt);
+    }
     if (wid == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -312,7 +325,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
         if (lane == 0) {
             uint32_t rc = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const int b = item / p.n_mtiles, y0 = (item - b * p.n_mtiles) * BM;
+                int b, mt;
+                item_to_tile(p, item, b, mt);
+                const int y0 = mt * BM;
                 for (int pass = 0; pass < p.npass; ++pass)
                     for (int ch = 0; ch < p.nchunks * RPC; ++ch, ++rc) {
                         const uint32_t rs = rc % SR, rph = (rc / SR) & 1u;
@@ -332,7 +347,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
             asm volatile("griddepcontrol.wait;" ::: "memory");
             uint32_t cc = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const int b = item / p.n_mtiles;
+                int b, mt;
+                item_to_tile(p, item, b, mt);
                 for (int pass = 0; pass < p.npass; ++pass)
                     for (int ch = 0; ch < p.nchunks; ++ch, ++cc) {
                         const uint32_t s = cc % SA, ph = (cc / SA) & 1u;
@@ -493,7 +509,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
         asm volatile("griddepcontrol.wait;" ::: "memory");                     // the per-token terms come from nc_prep_kernel too
         uint32_t it = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-            const int b = item / p.n_mtiles, y0 = (item - b * p.n_mtiles) * BM;
+            int b, mt;
+            item_to_tile(p, item, b, mt);
+            const int y0 = mt * BM;
             const uint32_t slot = two_slots ? (it & 1u) : 0u, use = two_slots ? (it >> 1) : it;
             const int y = y0 + row;
             const bool y_ok = y < p.Ty;
@@ -656,8 +674,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
             fence_before();
             mbar_arrive(bar_t_empty + 8 * slot);               // 128 arrivals: the accumulator may be overwritten
             if (wid == 11 && lane == 0) NC_STAMP(4, it, 2);
+            if (p.ready != nullptr) __threadfence();          // this thread's part of the tile is visible device-wide ...
             asm volatile("bar.sync 1, 128;" ::: "memory");    // every epilogue thread is done with this tile's per-token terms
+            if (p.ready != nullptr && wid == 11 && lane == 0)   // ... before the tile is published to the search running beside us
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.ready + (size_t)b * p.n_mtiles + mt), "r"(p.epoch) : "memory");
         }
+    }
+    if (kDbg && p.ready != nullptr && tid == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMax(reinterpret_cast<unsigned long long*>(p.ready + (size_t)p.B * p.n_mtiles + 64) + 1, gt);
     }
     fence_before();
     __syncthreads();
@@ -718,7 +743,8 @@ static int encode3(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void
 
 template <int MODE>
 static int run(const float* a_src, const float* b_src0, const float* b_src1, const float* prior, const int32_t* x_lengths, float* out, float temperature,
-               int b, int c, int tx, int ty, void* workspace, size_t workspace_bytes, cudaStream_t stream, const char* who)
+               int b, int c, int tx, int ty, void* workspace, size_t workspace_bytes, cudaStream_t stream, const char* who,
+               int* ready = nullptr, int epoch = 0, int max_ctas = 0)
 {
     Plan pl;
     if (!make_plan(MODE, b, c, tx, ty, &pl)) return ALB200_E_UNSUPPORTED;
@@ -757,10 +783,12 @@ static int run(const float* a_src, const float* b_src0, const float* b_src1, con
     p.temperature = temperature; p.B = b; p.C = c; p.Tx = tx; p.Ty = ty; p.NT = pl.NT; p.NB = pl.NB; p.npass = pl.npass; p.nchunks = pl.nchunks;
     p.n_mtiles = (ty + BM - 1) / BM; p.n_items = b * p.n_mtiles; p.sr = pl.sr;
     p.off_a = pl.off_a; p.off_b = pl.off_b; p.off_aux = pl.off_aux; p.b_stage_bytes = pl.b_stage;
-    const int grid = p.n_items < sms ? p.n_items : sms;
+    p.ready = ready; p.epoch = epoch; p.tile_major = ready != nullptr;
+    int grid = p.n_items < sms ? p.n_items : sms;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;     // the rest of the machine belongs to the search running beside us
     static long long* d_dbg = nullptr;
     const size_t dbg_n = 6 * kDbgSlots * 4;
-    if (kDbg && alb::opts().dbg) {
+    if (kDbg && alb::opts().dbg == 1) {
         if (!d_dbg) cudaMalloc(&d_dbg, dbg_n * 8);
         cudaMemsetAsync(d_dbg, 0, dbg_n * 8, stream);
         p.dbg = d_dbg;
@@ -814,6 +842,23 @@ extern "C" int alb200_neg_cent_gaussian_v2(const float* z, const float* m_p, con
                                            size_t workspace_bytes, void* stream)
 {
     return albv2::run<0>(z, m_p, logs_p, nullptr, nullptr, out, 0.f, b, c, tx, ty, workspace, workspace_bytes, (cudaStream_t)stream, "neg_cent_gaussian");
+}
+
+// Pipelined form for the fused neg_cent -> search entry (mas_api.cu): tiles in tile-major order on at most max_ctas SMs, each
+// published in ready[] (value = epoch) as soon as it is in global memory.
+extern "C" int alb200_neg_cent_gaussian_v2_pipelined(const float* z, const float* m_p, const float* logs_p, float* out, int b, int c, int tx, int ty,
+                                                     void* workspace, size_t workspace_bytes, void* stream, int* ready, int epoch, int max_ctas)
+{
+    return albv2::run<0>(z, m_p, logs_p, nullptr, nullptr, out, 0.f, b, c, tx, ty, workspace, workspace_bytes, (cudaStream_t)stream, "neg_cent_gaussian",
+                         ready, epoch, max_ctas);
+}
+
+extern "C" int alb200_neg_cent_ota_v2_pipelined(const float* queries, const float* keys, const float* prior, const int32_t* x_lengths, float* out,
+                                                float temperature, int b, int c, int tx, int ty, void* workspace, size_t workspace_bytes, void* stream,
+                                                int* ready, int epoch, int max_ctas)
+{
+    return albv2::run<1>(queries, keys, nullptr, prior, x_lengths, out, temperature, b, c, tx, ty, workspace, workspace_bytes, (cudaStream_t)stream,
+                         "neg_cent_ota", ready, epoch, max_ctas);
 }
 
 extern "C" int alb200_neg_cent_ota_v2(const float* queries, const float* keys, const float* prior, const int32_t* x_lengths, float* out, float temperature,

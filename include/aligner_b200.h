@@ -193,6 +193,28 @@ int alb200_neg_cent_ota_ws(const float *queries, const float *keys, const float 
                            const int32_t *x_lengths, float *out, float temperature,
                            int b, int c, int tx, int ty, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Fused score + search (the seam it removes is monotonic_align/__init__.py:11-14, where the reference
+ * materialises the score matrix, stages it and only then consumes it):
+ *   neg_cent = gaussian score of (z, m_p, logs_p)         [b, tx, ty], also returned (callers log it / reuse it)
+ *   paths    = monotonic alignment search over neg_cent    same contract as alb200_mas_device_ex (lengths or mask)
+ * in ONE call.  When the search leaves SMs free (batch <= #SM: one CTA or cluster per utterance) the two kernels run
+ * CONCURRENTLY: the score kernel produces 128-frame tiles in the order the search consumes them, on the free SMs, and
+ * publishes each tile; the search is launched programmatically dependent, starts beside it and its loader warps wait
+ * per tile, so a tile is read out of L2 while the next ones are still being computed.  Results are bit-identical to
+ * alb200_neg_cent_gaussian followed by alb200_mas_device_ex (same kernels, same values).  Larger batches run the two
+ * kernels back to back.  workspace: alb200_fused_workspace_bytes() bytes, 256-byte aligned, ZERO when first handed
+ * over and private to this (device, stream) afterwards.
+ * ------------------------------------------------------------------------ */
+size_t alb200_fused_workspace_bytes(int b, int c, int tx, int ty);
+int alb200_gaussian_mas_fused(const float *z, const float *m_p, const float *logs_p, float *neg_cent,
+                              const int32_t *t_xs, const int32_t *t_ys,
+                              const void *mask, int mask_dtype, int64_t mask_stride_b, int64_t mask_stride_x, int64_t mask_stride_y,
+                              void *paths, int path_elem_size, uint64_t path_one, int zero_fill,
+                              int32_t *frame_tok, int32_t *durations,
+                              int b, int c, int tx, int ty, float max_neg_val,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
 /* Number of kernels this library has launched on this thread since load. */
 uint64_t alb200_launch_count(void);
 
