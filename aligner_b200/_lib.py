@@ -26,7 +26,7 @@ SYMBOLS = (
     "alb200_last_transfer_bytes", "alb200_launch_count",
     "alb200_neg_cent_gaussian", "alb200_neg_cent_ota",
     "alb200_neg_cent_workspace_bytes", "alb200_neg_cent_gaussian_ws", "alb200_neg_cent_ota_ws",
-    "alb200_fused_workspace_bytes", "alb200_gaussian_mas_fused",
+    "alb200_fused_workspace_bytes", "alb200_gaussian_mas_fused", "alb200_neg_cent_ota_bb",
 )
 
 
@@ -76,6 +76,8 @@ def _load() -> ctypes.CDLL:
     lib.alb200_neg_cent_gaussian_ws.restype = i32
     lib.alb200_neg_cent_ota_ws.argtypes = [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp, sz, vp]
     lib.alb200_neg_cent_ota_ws.restype = i32
+    lib.alb200_neg_cent_ota_bb.argtypes = [vp, vp, vp, vp, f32, vp, f32, i32, i32, i32, i32, vp, sz, vp]
+    lib.alb200_neg_cent_ota_bb.restype = i32
     lib.alb200_fused_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.alb200_fused_workspace_bytes.restype = sz
     lib.alb200_gaussian_mas_fused.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i64, i64, i64, vp, i32, u64, i32, vp, vp,

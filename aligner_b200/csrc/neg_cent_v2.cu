@@ -264,6 +264,8 @@ struct V2Params {
     const float* inv_sb;       // [b, NT] inverse row scale (gaussian) / 2 T / row scale (ota)
     const float* prior;        // ota: optional [b, Tx, Ty]
     const int32_t* x_lengths;  // ota: optional [b]
+    const int32_t* y_lengths;  // ota, generated prior: optional [b] mel lengths
+    float prior_scaling;       // ota: > 0 = beta-binomial prior generated in the epilogue instead of read from `prior`
     float* out;                // [b, Tx, Ty]
     float temperature;
     int B, C, Tx, Ty;
@@ -622,6 +624,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                     }
                     const float lse = mx + fast_log2(sm) * LN2;
                     float* o = ob;
+                    if (p.prior_scaling > 0.f) {
+                        // Beta-binomial alignment prior of the OTA paper, generated here instead of read from a [b, t_x, t_y] tensor:
+                        //   prior[x, y] = BetaBinom(x; n = t_x - 1, a = s (y + 1), b = s (t_y - y))        (oracle/neg_cent.py:beta_binomial_prior)
+                        // This thread owns frame y and walks the tokens in order, so the pmf is a recurrence along x,
+                        //   pmf(x + 1) / pmf(x) = (n - x)(x + a) / ((x + 1)(n - x - 1 + b)),   pmf(0) = B(a, n + b) / B(a, b),
+                        // one division and one logarithm per cell; the start value needs four lgamma in fp64 per frame (their sizes,
+                        // ~1e4, cancel to ~1e1: fp32 would lose the 1e-5 bound).  Frames past t_y get prior 0, i.e. log(1e-8), what a
+                        // zero-padded prior tensor gives.
+                        const int tyl = p.y_lengths ? min(max(p.y_lengths[b], 0), Ty) : Ty;
+                        const int n = tlen - 1;
+                        const bool inb = y < tyl;
+                        const float af = p.prior_scaling * (float)(y + 1), bf = p.prior_scaling * (float)(tyl - y);
+                        double lp = 0.0;                                          // fp64 running sum: 300 fp32 roundings at |lp| ~ 50 would cost the 1e-5 bound
+                        if (inb && n > 0) {
+                            const double a = (double)p.prior_scaling * (double)(y + 1), bq = (double)p.prior_scaling * (double)(tyl - y);
+                            lp = lgamma((double)n + bq) + lgamma(a + bq) - lgamma((double)n + a + bq) - lgamma(bq);
+                        }
+                        const float lzero = -18.420680743952367f;                 // log(1e-8)
+                        for (int g = 0; g < ngroups; ++g) {
+                            NC_LOAD_TERMS(g)
+                            uint32_t r[16];
+                            tmem_ld16(tcol + (uint32_t)(16 * g), r);
+                            if (y_ok) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const int xl = 16 * g + j;
+                                    if (xl < Tx) {
+                                        float v = -INFINITY;        // text padding is excluded from the softmax
+                                        if (xl < tlen) {
+                                            v = fmaf(__uint_as_float(r[j]), ss[j], cc[j]) - lse + (inb ? logf(expf((float)lp) + 1e-8f) : lzero);
+                                            const float num = (float)(n - xl) * ((float)xl + af), den = (float)(xl + 1) * ((float)(n - xl - 1) + bf);
+                                            lp += (double)logf(num / den);        // x = n: log(0) = -inf, never used again
+                                        }
+                                        *o = v; o += Ty;
+                                    }
+                                }
+                            }
+                        }
+                    } else
                     for (int g = 0; g < ngroups; ++g) {
                         NC_LOAD_TERMS(g)
                         uint32_t r[16];
@@ -663,7 +704,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                             }
                             if (!ps) { const float nm = fmaxf(mx, v); sm = sm * expf(mx - nm) + expf(v - nm); mx = nm; }
                             else {
-                                if (x < tlen) { v -= lse; if (pr) v += logf(pr[(size_t)x * Ty] + 1e-8f); }
+                                if (x < tlen) {
+                                    v -= lse;
+                                    if (pr) v += logf(pr[(size_t)x * Ty] + 1e-8f);
+                                    if (p.prior_scaling > 0.f) {                     // generated prior, straight from the definition (exact path: speed is irrelevant)
+                                        const int tyl = p.y_lengths ? min(max(p.y_lengths[b], 0), Ty) : Ty;
+                                        const int n = tlen - 1;
+                                        double pm = 0.0;
+                                        if (y < tyl) {
+                                            const double a = (double)p.prior_scaling * (y + 1), bq = (double)p.prior_scaling * (tyl - y);
+                                            pm = exp(lgamma(n + 1.0) - lgamma(x + 1.0) - lgamma(n - x + 1.0) + lgamma(x + a) + lgamma(n - x + bq) - lgamma(n + a + bq)
+                                                     - (lgamma(a) + lgamma(bq) - lgamma(a + bq)));
+                                        }
+                                        v += (float)log(pm + 1e-8);
+                                    }
+                                }
                                 ob[(size_t)x * Ty] = v;
                             }
                         }
@@ -744,7 +799,7 @@ static int encode3(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void
 template <int MODE>
 static int run(const float* a_src, const float* b_src0, const float* b_src1, const float* prior, const int32_t* x_lengths, float* out, float temperature,
                int b, int c, int tx, int ty, void* workspace, size_t workspace_bytes, cudaStream_t stream, const char* who,
-               int* ready = nullptr, int epoch = 0, int max_ctas = 0)
+               int* ready = nullptr, int epoch = 0, int max_ctas = 0, const int32_t* y_lengths = nullptr, float prior_scaling = 0.f)
 {
     Plan pl;
     if (!make_plan(MODE, b, c, tx, ty, &pl)) return ALB200_E_UNSUPPORTED;
@@ -784,6 +839,7 @@ static int run(const float* a_src, const float* b_src0, const float* b_src1, con
     p.n_mtiles = (ty + BM - 1) / BM; p.n_items = b * p.n_mtiles; p.sr = pl.sr;
     p.off_a = pl.off_a; p.off_b = pl.off_b; p.off_aux = pl.off_aux; p.b_stage_bytes = pl.b_stage;
     p.ready = ready; p.epoch = epoch; p.tile_major = ready != nullptr;
+    p.y_lengths = y_lengths; p.prior_scaling = prior_scaling;
     int grid = p.n_items < sms ? p.n_items : sms;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;     // the rest of the machine belongs to the search running beside us
     static long long* d_dbg = nullptr;
@@ -859,6 +915,21 @@ extern "C" int alb200_neg_cent_ota_v2_pipelined(const float* queries, const floa
 {
     return albv2::run<1>(queries, keys, nullptr, prior, x_lengths, out, temperature, b, c, tx, ty, workspace, workspace_bytes, (cudaStream_t)stream,
                          "neg_cent_ota", ready, epoch, max_ctas);
+}
+
+// OTA score with the beta-binomial prior generated in the epilogue (no [b, t_x, t_y] prior read).  ALB200_E_UNSUPPORTED for
+// shapes this generation does not take: the caller materialises the prior and uses alb200_neg_cent_ota_ws.
+extern "C" int alb200_neg_cent_ota_bb(const float* queries, const float* keys, const int32_t* x_lengths, const int32_t* y_lengths, float prior_scaling,
+                                      float* out, float temperature, int b, int c, int tx, int ty, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (!queries || !keys || !out || b < 0 || c <= 0 || tx <= 0 || ty <= 0 || !(prior_scaling > 0.f)) {
+        snprintf(alb::g_err, sizeof(alb::g_err), "neg_cent_ota_bb: null pointer, bad shape or non-positive prior scaling");
+        return ALB200_E_INVALID;
+    }
+    if (b == 0) return 0;
+    if (!workspace || alb::opts().nc_ffma || alb::opts().nc_v1) return ALB200_E_UNSUPPORTED;
+    return albv2::run<1>(queries, keys, nullptr, nullptr, x_lengths, out, temperature, b, c, tx, ty, workspace, workspace_bytes, (cudaStream_t)stream,
+                         "neg_cent_ota_bb", nullptr, 0, 0, y_lengths, prior_scaling);
 }
 
 extern "C" int alb200_neg_cent_ota_v2(const float* queries, const float* keys, const float* prior, const int32_t* x_lengths, float* out, float temperature,

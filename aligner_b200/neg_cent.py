@@ -53,11 +53,32 @@ def gaussian_neg_cent(z: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor) 
     return out
 
 
+def beta_binomial_prior(x_lengths: torch.Tensor, y_lengths: torch.Tensor, tx: int, ty: int, scaling: float = 1.0) -> torch.Tensor:
+    """Dense [b, t_x, t_y] beta-binomial alignment prior (OTA paper; oracle/neg_cent.py:beta_binomial_prior), zero outside each
+    utterance's lengths.  Only needed on the paths that cannot generate it inside the kernel; computed on the device in fp64."""
+    dev = x_lengths.device
+    xl = x_lengths.to(torch.float64)[:, None, None]
+    yl = y_lengths.to(torch.float64)[:, None, None]
+    x = torch.arange(tx, device=dev, dtype=torch.float64)[None, :, None]
+    y = torch.arange(ty, device=dev, dtype=torch.float64)[None, None, :]
+    n, a, bq = xl - 1, scaling * (y + 1), scaling * (yl - y)
+    valid = (x < xl) & (y < yl)
+    lg = torch.lgamma
+    safe = lambda t: torch.where(valid, t, torch.ones_like(t))
+    lp = (lg(safe(n + 1)) - lg(safe(x + 1)) - lg(safe(n - x + 1)) + lg(safe(x + a)) + lg(safe(n - x + bq)) - lg(safe(n + a + bq))
+          - (lg(safe(a)) + lg(safe(bq)) - lg(safe(a + bq))))
+    return torch.where(valid, torch.exp(lp), torch.zeros_like(lp)).to(torch.float32)
+
+
 def ota_log_prob(queries: torch.Tensor, keys: torch.Tensor, temperature: float = 0.0005, prior: torch.Tensor | None = None,
-                 x_lengths: torch.Tensor | None = None) -> torch.Tensor:
+                 x_lengths: torch.Tensor | None = None, *, y_lengths: torch.Tensor | None = None,
+                 prior_scaling: float | None = None) -> torch.Tensor:
     """queries [b,c,t_mel], keys [b,c,t_text]  ->  [b,t_text,t_mel] fp32:
     log_softmax over the text axis of -temperature * ||q - k||^2, plus log(prior + 1e-8) if given
-    (OTA aligner, arXiv 2108.10447; NeMo AlignmentEncoder)."""
+    (OTA aligner, arXiv 2108.10447; NeMo AlignmentEncoder).
+
+    prior_scaling=s (with x_lengths / y_lengths): the beta-binomial prior BetaBinom(x; t_x - 1, s (y + 1), s (t_y - y)) is
+    generated inside the kernel instead of being read from a [b, t_x, t_y] tensor."""
     q, k = _f32c(queries, "queries"), _f32c(keys, "keys")
     if q.dim() != 3 or k.dim() != 3 or q.shape[:2] != k.shape[:2]:
         raise ValueError("expected queries [b,c,t_y], keys [b,c,t_x]; got %s %s" % (tuple(q.shape), tuple(k.shape)))
@@ -71,8 +92,25 @@ def ota_log_prob(queries: torch.Tensor, keys: torch.Tensor, temperature: float =
     xl = None
     if x_lengths is not None:
         xl = x_lengths.to(device=q.device, dtype=torch.int32).contiguous()
+    yl = None
+    if y_lengths is not None:
+        yl = y_lengths.to(device=q.device, dtype=torch.int32).contiguous()
+    if prior_scaling is not None and prior is not None:
+        raise ValueError("give either a prior tensor or prior_scaling, not both")
     with torch.cuda.device(q.device):
         out = torch.empty((b, tx, ty), dtype=torch.float32, device=q.device)
+        if b and tx and ty and prior_scaling is not None:
+            ws, need = _scratch(1, b, c, tx, ty, q.device)
+            rc = _lib.lib.alb200_neg_cent_ota_bb(q.data_ptr(), k.data_ptr(), xl.data_ptr() if xl is not None else None,
+                                                 yl.data_ptr() if yl is not None else None, float(prior_scaling), out.data_ptr(),
+                                                 float(temperature), b, c, tx, ty, ws.data_ptr() if ws is not None else None, need,
+                                                 torch.cuda.current_stream(q.device).cuda_stream)
+            if rc == 0:
+                return out
+            if rc != _lib.E_UNSUPPORTED:
+                _lib.check(rc)
+            full = lambda t, n: t if t is not None else torch.full((b,), n, dtype=torch.int32, device=q.device)
+            pr = beta_binomial_prior(full(xl, tx), full(yl, ty), tx, ty, float(prior_scaling))      # materialised for the other paths
         if b and tx and ty:
             ws, need = _scratch(1, b, c, tx, ty, q.device)
             _lib.check(_lib.lib.alb200_neg_cent_ota_ws(q.data_ptr(), k.data_ptr(), pr.data_ptr() if pr is not None else None,

@@ -193,6 +193,16 @@ int alb200_neg_cent_ota_ws(const float *queries, const float *keys, const float 
                            const int32_t *x_lengths, float *out, float temperature,
                            int b, int c, int tx, int ty, void *workspace, size_t workspace_bytes, void *stream);
 
+/* OTA score with the beta-binomial alignment prior of the OTA paper GENERATED inside the kernel instead of
+ * read from a [b, tx, ty] tensor:  prior[b, x, y] = BetaBinom(x; n = t_x[b] - 1, a = s (y + 1), b = s (t_y[b] - y)) for
+ * y < t_y[b], 0 beyond (what a zero-padded prior tensor holds); out = log_softmax_x(d) + log(prior + 1e-8).
+ * x_lengths / y_lengths: optional int32 [b] (NULL = tx / ty), s = prior_scaling > 0.  Same workspace as
+ * alb200_neg_cent_ota_ws.  ALB200_E_UNSUPPORTED for shapes outside the TMA / tcgen05 path (tx > 512, ty % 4 != 0): the
+ * caller then materialises the prior and uses alb200_neg_cent_ota_ws (the Python layer does). */
+int alb200_neg_cent_ota_bb(const float *queries, const float *keys, const int32_t *x_lengths, const int32_t *y_lengths,
+                           float prior_scaling, float *out, float temperature, int b, int c, int tx, int ty,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------
  * Fused score + search (the seam it removes is monotonic_align/__init__.py:11-14, where the reference
  * materialises the score matrix, stages it and only then consumes it):

@@ -145,6 +145,33 @@ def test_mel_side_outside_fp16_range_is_recomputed_exactly(nc, scale, expect_exa
         assert torch.isnan(got[0, :, 7]).all() and torch.isfinite(got[0, :, 8]).all() and torch.isfinite(got[1]).all()
 
 
+@pytest.mark.parametrize("b,c,tx,ty,scaling,native", [(3, 80, 60, 200, 1.0, True), (2, 80, 300, 1500, 1.0, True), (2, 40, 37, 132, 0.5, True),
+                                                       (2, 16, 600, 640, 1.0, False),          # t_x > 512: prior materialised on the device
+                                                       (2, 16, 50, 131, 2.0, False)])          # t_mel % 4 != 0: same
+def test_ota_with_generated_beta_binomial_prior(nc, b, c, tx, ty, scaling, native):
+    """the OTA prior BetaBinom(x; t_x - 1, s (y + 1), s (t_y - y)) generated inside the kernel against the
+    fp64 oracle fed the dense scipy prior (oracle/neg_cent.py:beta_binomial_prior), ragged lengths."""
+    from aligner_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(41 + tx)
+    q = torch.randn(b, c, ty, generator=g, device="cuda")
+    k = torch.randn(b, c, tx, generator=g, device="cuda")
+    rng = np.random.default_rng(41 + tx)
+    t_x = rng.integers(max(2, tx // 2), tx + 1, b).astype(np.int32)
+    t_y = np.array([rng.integers(max(t_x[i], ty // 2), ty + 1) for i in range(b)], np.int32)
+    t_x[0], t_y[0] = tx, ty
+    dense = np.zeros((b, tx, ty))
+    for i in range(b):
+        dense[i, :t_x[i], :t_y[i]] = nc_oracle.beta_binomial_prior(int(t_x[i]), int(t_y[i]), scaling)
+    want = nc_oracle.ota_log_prob(q.cpu().numpy(), k.cpu().numpy(), 0.0005, dense, t_x)
+    n0 = _lib.launch_count()
+    got = nc.ota_log_prob(q, k, 0.0005, x_lengths=torch.from_numpy(t_x).cuda(), y_lengths=torch.from_numpy(t_y).cuda(), prior_scaling=scaling)
+    assert (_lib.launch_count() - n0 == 2) == native        # prep + score kernel, no other launch of ours: the prior was never materialised
+    assert rel_err(got.cpu().numpy(), want) <= TOL
+    # the dense prior built on the device for the other paths is the same function
+    mine = nc.beta_binomial_prior(torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda(), tx, ty, scaling).cpu().numpy()
+    assert np.abs(mine - dense).max() <= 1e-6
+
+
 def test_c_entry_without_workspace(nc):
     """alb200_neg_cent_gaussian / _ota (no scratch argument) take the scratch from the stream-ordered allocator."""
     from aligner_b200 import _lib
