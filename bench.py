@@ -361,14 +361,48 @@ def bench_neg_cent(torch, dev, timer, ma, lib, peak_tflops):
     err = float(np.abs(score[:2].cpu().numpy() - ref).max() / np.abs(ref).max())
     flop = 2.0 * 2 * c * b * tx * ty
     pms, _, _ = timer.run(pipe_step, 20)
+    import aligner_b200.fused as fused
+    xl = torch.full((b,), tx, dtype=torch.int32, device=dev)
+    yl = torch.full((b,), ty, dtype=torch.int32, device=dev)
+
+    def fused_step(i):
+        keep[i % 4] = fused.gaussian_maximum_path(z, m, logs, x_lengths=xl, y_lengths=yl)
+
+    fms, flaunches, _ = timer.run(fused_step, 20)
+    fpath, fscore = fused.gaussian_maximum_path(z, m, logs, x_lengths=xl, y_lengths=yl)
+    fused_ok = bool(torch.equal(fscore, score) and torch.equal(fpath, ma.maximum_path(score, ones)))
     out["gaussian_c2"] = {"shape": "B=%d C=%d T_text=%d T_mel=%d" % (b, c, tx, ty), "us": ms * 1e3, "launches_per_call": launches // 20 if launches else None,
                           "algorithmic_tflops": flop / (ms * 1e-3) / 1e12, "algorithmic_flop_per_cell": 4 * c,
                           "executed_tflops_3x_split": 3 * flop / (ms * 1e-3) / 1e12,
                           "max_rel_err_vs_fp64": err, "tolerance": 1e-5,
                           "tensor_pipe_source": "profiles/r02_nc_gauss.summary.txt (ncu --set full of this kernel; not measurable inside a timed run)",
                           "peak_bf16_tflops_measured": peak_tflops,
-                          "pipeline_neg_cent_plus_mas_us": pms * 1e3}
-    del z, m, logs, score
+                          "pipeline_neg_cent_plus_mas_us": pms * 1e3,
+                          "fused_entry_us": fms * 1e3, "fused_entry_launches": flaunches // 20 if flaunches else None,
+                          "fused_entry_mode": "back to back (64 utterances need 64 of 148 SMs: pipelining measured no gain, DESIGN.md)",
+                          "fused_bit_identical_to_separate_calls": fused_ok}
+    # ---- the pipelined form of the fused entry pays when the search needs at most a third of the SMs: C3's shape with the Gaussian score
+    b3, tx3, ty3 = 32, 300, 1500
+    z3 = torch.randn(b3, c, ty3, generator=g, device=dev)
+    m3 = torch.randn(b3, c, tx3, generator=g, device=dev)
+    l3 = torch.rand(b3, c, tx3, generator=g, device=dev) * 1.5 - 1.0
+    xl3 = torch.full((b3,), tx3, dtype=torch.int32, device=dev)
+    yl3 = torch.full((b3,), ty3, dtype=torch.int32, device=dev)
+
+    def sep3(i):
+        keep[i % 4] = ma.maximum_path_lengths(nc.gaussian_neg_cent(z3, m3, l3), xl3, yl3)["path"]
+
+    def fus3(i):
+        keep[i % 4] = fused.gaussian_maximum_path(z3, m3, l3, x_lengths=xl3, y_lengths=yl3)
+
+    s3, _, _ = timer.run(sep3, 20)
+    f3, _, _ = timer.run(fus3, 20)
+    p3, sc3 = fused.gaussian_maximum_path(z3, m3, l3, x_lengths=xl3, y_lengths=yl3)
+    ok3 = bool(torch.equal(sc3, nc.gaussian_neg_cent(z3, m3, l3)) and torch.equal(p3, ma.maximum_path_lengths(sc3, xl3, yl3)["path"]))
+    out["fused_gaussian_32x192x300x1500"] = {"separate_calls_us": s3 * 1e3, "fused_entry_us": f3 * 1e3,
+                                             "fused_entry_mode": "pipelined: score kernel on 116 SMs publishes 128-frame tiles, the search runs beside it",
+                                             "fused_bit_identical_to_separate_calls": ok3}
+    del z, m, logs, score, z3, m3, l3
     # ---- OTA, C3
     b, c, tx, ty = 32, 80, 300, 1500
     q = torch.randn(b, c, ty, generator=g, device=dev)
@@ -492,6 +526,24 @@ def strong_scaling_c5(torch, dist, dev, ma, lib, rank, world, peak, total_b=8192
             "durations_allgather_verified": bool(okt.item()), "oracle_sample_ok": oracle_ok}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Multi-rank runs: keep this rank's threads (and, by first touch, its pinned staging buffers) on the NUMA node of its GPU so
+    that eight ranks' host-to-device streams do not all cross the same memory controller.  Returns the CPU list or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + bit for w, m in enumerate(mask) for bit in range(64) if (m >> bit) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------- ours
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
@@ -499,6 +551,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -671,6 +724,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "e2e": {"value": e2e_val, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "maximum_path_c(paths, values, t_xs, t_ys) with pinned host numpy buffers", "ms_per_step": float(te.item()) * 1e3,
                     "per_rank_ms": [float(x.item()) * 1e3 for x in per_rank_e2e],
+                    "rank0_cpu_affinity": ("%d cpus of the GPU's NUMA node" % len(numa_cpus)) if numa_cpus else "unchanged",
                     "h2d_GBps_per_rank": [h2d / float(x.item()) / 1e9 for x in per_rank_e2e],
                     "paths_match_device_api": host_ok},
             "e2e_device_api": e2e_dev,
