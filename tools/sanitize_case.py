@@ -20,6 +20,18 @@ for force, b, tx, ty, dt in CASES:
     torch.cuda.synchronize()
     assert int(out["durations"].sum()) == int(t_y.sum())
 _lib.set_option("force", None)
+# second-generation score kernels (TMA / tcgen05, both accumulator modes), generated prior, fused pipelined entry
+import aligner_b200.fused as fused
+for (b, c, tx, ty) in [(3, 40, 150, 300), (2, 80, 300, 520)]:
+    z2 = torch.randn(b, c, ty, device="cuda"); m2 = torch.randn(b, c, tx, device="cuda"); l2 = torch.rand(b, c, tx, device="cuda") - 0.5
+    g2 = nc.gaussian_neg_cent(z2, m2, l2); o2 = nc.ota_log_prob(z2, m2, 0.0005)
+    xl = torch.full((b,), tx - 3, dtype=torch.int32, device="cuda"); yl = torch.full((b,), ty - 5, dtype=torch.int32, device="cuda")
+    o3 = nc.ota_log_prob(z2, m2, 0.0005, x_lengths=xl, y_lengths=yl, prior_scaling=1.0)
+    _lib.set_option("fused_seq", "2")
+    pth, sc = fused.gaussian_maximum_path(z2, m2, l2, x_lengths=xl, y_lengths=yl)
+    _lib.set_option("fused_seq", None)
+    torch.cuda.synchronize()
+    assert torch.equal(sc, g2) and int(pth.sum()) == int(yl.sum())
 z = torch.randn(2, 40, 300, device="cuda"); m = torch.randn(2, 40, 150, device="cuda"); lg = torch.rand(2, 40, 150, device="cuda") - 0.5
 s = nc.gaussian_neg_cent(z, m, lg); q = nc.ota_log_prob(torch.randn(2, 80, 300, device="cuda"), torch.randn(2, 80, 150, device="cuda"))
 torch.cuda.synchronize()
