@@ -48,7 +48,8 @@ constexpr int A_TILE = BM * 128;              // 16 KB: 128 rows x one swizzled 
 constexpr int SA = 2;                         // A / B stages
 constexpr int NTHREADS = 15 * 32;             // warp 0 raw-box TMA, warp 1 MMA, warp 2 text-operand TMA, warps 3-10 transform, warps 11-14 epilogue
 constexpr int N_TRANSFORM = 256;
-constexpr int AUX_BYTES = 256 + 2 * 512 * 4;  // barriers, tmem slot, per-tile flags (256 B), then the tile's per-token terms [2][512] fp32
+constexpr int AUX_BYTES = 256 + 2 * 512 * 4 + 3 * 128 * 8;  // barriers, tmem slot, per-tile flags (256 B), the tile's per-token terms [2][512] fp32,
+                                                            // and the log-sum-exp partials of the three warps of a TMEM quadrant (ota, long texts)
 constexpr float kZLimit = 500.f, kQLimit = 1000.f;
 // fixed mel-side factors (exact powers of two) and their inverses on the text side
 constexpr float kA1 = -0.5f * 0.25f;          // -0.5 z^2 * 2^-2
@@ -281,6 +282,86 @@ __device__ __forceinline__ void item_to_tile(const V2Params& p, int item, int& b
     else { b = item / p.n_mtiles; mt = item - b * p.n_mtiles; }
 }
 
+// OTA epilogue, fast path, for one thread = one mel frame (TMEM lane).  d'[x] = acc * (2T / scale_x) - T |k_x|^2  (|q_y|^2 is
+// constant along the softmax axis and cancels).  Pass 1: log-sum-exp over the text axis, one dependent step per 16 tokens (group
+// maximum first, then 16 independent exponentials); pass 2: normalise (+ prior tensor) and store.  nparts > 1: the token groups
+// of the tile are dealt round-robin to the `nparts` warps that share this TMEM quadrant (texts longer than 256 tokens fill both
+// accumulator halves, nothing overlaps the epilogue, so the transform warps help); their partial (max, sum) pairs meet in xch.
+__device__ __forceinline__ void ota_fast_part(uint32_t tcol, const float4* colv4, const float4* isb4, float* xch, int part, int nparts, int row,
+                                              bool y_ok, int Tx, int Ty, int NT, int tlen, const float* pr, float* ob)
+{
+    constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+#define NC_LOAD_TERMS2(g)                                                                                                     \
+    float cc[16], ss[16];                                                                                                      \
+    _Pragma("unroll") for (int j4 = 0; j4 < 4; ++j4) {                                                                         \
+        const float4 c4 = colv4[4 * (g) + j4], s4 = isb4[4 * (g) + j4];                                                        \
+        cc[4 * j4] = c4.x; cc[4 * j4 + 1] = c4.y; cc[4 * j4 + 2] = c4.z; cc[4 * j4 + 3] = c4.w;                                \
+        ss[4 * j4] = s4.x; ss[4 * j4 + 1] = s4.y; ss[4 * j4 + 2] = s4.z; ss[4 * j4 + 3] = s4.w;                                \
+    }
+    float mx = -INFINITY, sm = 0.f;
+    const int gl = (tlen + 15) >> 4, ngroups = NT >> 4;
+    for (int g = part; g < gl; g += nparts) {
+        NC_LOAD_TERMS2(g)
+        uint32_t r[16];
+        tmem_ld16(tcol + (uint32_t)(16 * g), r);
+        float d[16], gm = -INFINITY;
+        if (16 * g + 16 <= tlen) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { d[j] = fmaf(__uint_as_float(r[j]), ss[j], cc[j]); gm = fmaxf(gm, d[j]); }
+        } else {
+            const int nv = tlen - 16 * g;                          // >= 1
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { d[j] = (j < nv) ? fmaf(__uint_as_float(r[j]), ss[j], cc[j]) : -INFINITY; gm = fmaxf(gm, d[j]); }
+        }
+        const float nm = fmaxf(mx, gm);
+        const float nml = nm * L2E;
+        float psum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) psum += fast_exp2(fmaf(d[j], L2E, -nml));   // 2^-inf = 0 for the padding
+        sm = fmaf(sm, fast_exp2((mx - nm) * L2E), psum);
+        mx = nm;
+    }
+    if (nparts > 1) {
+        xch[(part * BM + row) * 2] = mx; xch[(part * BM + row) * 2 + 1] = sm;
+        asm volatile("bar.sync 2, 384;" ::: "memory");
+        float gm = -INFINITY;
+        for (int q = 0; q < nparts; ++q) gm = fmaxf(gm, xch[(q * BM + row) * 2]);
+        float tot = 0.f;
+        for (int q = 0; q < nparts; ++q) {
+            const float mq = xch[(q * BM + row) * 2], sq = xch[(q * BM + row) * 2 + 1];
+            if (sq > 0.f) tot = fmaf(sq, fast_exp2((mq - gm) * L2E), tot);      // a part without tokens holds (-inf, 0)
+        }
+        mx = gm; sm = tot;
+    }
+    const float lse = mx + fast_log2(sm) * LN2;
+    for (int g = part; g < ngroups; g += nparts) {
+        NC_LOAD_TERMS2(g)
+        uint32_t r[16];
+        tmem_ld16(tcol + (uint32_t)(16 * g), r);
+        if (y_ok) {
+            float* o = ob + (size_t)(16 * g) * Ty;
+            if (16 * g + 16 <= tlen && pr == nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { *o = fmaf(__uint_as_float(r[j]), ss[j], cc[j]) - lse; o += Ty; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int xl = 16 * g + j;
+                    if (xl < Tx) {
+                        float v = -INFINITY;        // text padding is excluded from the softmax
+                        if (xl < tlen) {
+                            v = fmaf(__uint_as_float(r[j]), ss[j], cc[j]) - lse;
+                            if (pr) v += __logf(pr[(size_t)xl * Ty] + 1e-8f);
+                        }
+                        *o = v; o += Ty;
+                    }
+                }
+            }
+        }
+    }
+#undef NC_LOAD_TERMS2
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, const __grid_constant__ CUtensorMap map_a,
                                                             const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo)
@@ -309,7 +390,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
     if (tid == 0) {
         for (int s = 0; s < 4; ++s) { mbar_init(bar_raw_full + 8 * s, 1); mbar_init(bar_raw_empty + 8 * s, N_TRANSFORM / 32); }
         for (int s = 0; s < SA; ++s) { mbar_init(bar_a_full + 8 * s, N_TRANSFORM); mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_ab_empty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, (MODE == 1 && p.npass > 1 && !(p.prior_scaling > 0.f)) ? 384 : 128); }
         for (int s = 0; s < 8; ++s) ovf[s] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -321,6 +402,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
 
     const int K = MODE == 0 ? 2 * p.C : p.C;
     const int two_slots = (p.npass == 1);
+    // OTA with a text longer than 256 tokens: one accumulator spanning both TMEM halves, so the epilogue overlaps nothing and the
+    // eight transform warps (idle by then) take two thirds of it (not with the generated prior: its recurrence walks every token)
+    const bool helpers = (MODE == 1) && !two_slots && !(p.prior_scaling > 0.f);
+    float* xch = reinterpret_cast<float*>(smem + p.off_aux + 256 + 2 * 512 * 4);
 
     if (wid == 0) {
         // ================= TMA producer, mel side: raw z / q boxes (HBM latency: runs as far ahead as the ring allows) =================
@@ -500,6 +585,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                 if (last_of_item) bad = false;                                // the next chunk belongs to the next tile
                 if (!last_of_item || item + (int)gridDim.x < p.n_items) produce();
             }
+            if (MODE == 1 && helpers) {
+                // this tile's operand is complete (and the next tile's first chunk sits converted in registers): help with its epilogue
+                int b, mt;
+                item_to_tile(p, item, b, mt);
+                const int q4 = wid & 3, hrow = 32 * q4 + lane, y = mt * BM + hrow;
+                const bool y_ok = y < p.Ty;
+                const float* tokc = reinterpret_cast<const float*>(smem + p.off_aux + 256);
+                asm volatile("bar.sync 2, 384;" ::: "memory");                 // the epilogue warps have staged the per-token terms
+                mbar_wait(bar_t_full, it & 1u);
+                fence_after();
+                const bool slow = ovf[it & 7] != 0;
+                const int tlen = p.x_lengths ? min(max(p.x_lengths[b], 0), p.Tx) : p.Tx;
+                if (!slow)
+                    ota_fast_part(tmem_base + ((uint32_t)(32 * q4) << 16), reinterpret_cast<const float4*>(tokc), reinterpret_cast<const float4*>(tokc + 512), xch,
+                                  (wid - 3) >> 2, 3, hrow, y_ok, p.Tx, p.Ty, p.NT, tlen,
+                                  p.prior ? p.prior + (size_t)b * p.Tx * p.Ty + (y_ok ? y : 0) : nullptr, p.out + (size_t)b * p.Tx * p.Ty + (y_ok ? y : 0));
+                else
+                    asm volatile("bar.sync 2, 384;" ::: "memory");             // (the exact path is the epilogue warps' alone; keep the barrier count)
+                fence_before();
+                mbar_arrive(bar_t_empty);
+                if (p.ready != nullptr) __threadfence();
+                asm volatile("bar.sync 2, 384;" ::: "memory");                 // everybody is done with the per-token terms and the partials
+            }
         }
     } else {
         // ================= epilogue warps: TMEM -> registers -> global =================
@@ -524,7 +632,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                 const float* gc = p.colv + (size_t)b * p.NT;
                 const float* gs = p.inv_sb + (size_t)b * p.NT;
                 for (int i = et; i < p.NT; i += 128) { tokc[i] = __ldg(gc + i); toks[i] = __ldg(gs + i); }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (helpers) asm volatile("bar.sync 2, 384;" ::: "memory");
+                else asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             const float4* colv4 = reinterpret_cast<const float4*>(tokc);
             const float4* isb4 = reinterpret_cast<const float4*>(toks);
@@ -596,9 +705,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                 const int tlen = p.x_lengths ? min(max(p.x_lengths[b], 0), Tx) : Tx;
                 const float* pr = p.prior ? p.prior + (size_t)b * Tx * Ty + (y_ok ? y : 0) : nullptr;
                 constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-                if (!slow) {
-                    // d'[x] = acc * (2T / scale_x) - T |k_x|^2   (|q_y|^2 cancels in the log-softmax).  Pass 1: log-sum-exp over the text
-                    // axis, one dependent step per 16 tokens (group maximum first, then 16 independent exponentials).
+                if (!slow && !(p.prior_scaling > 0.f)) {
+                    ota_fast_part(tcol, colv4, isb4, xch, helpers ? 2 : 0, helpers ? 3 : 1, row, y_ok, Tx, Ty, p.NT, tlen, pr, ob);
+                } else if (!slow) {
+                    // generated beta-binomial prior: this thread walks every token in order
                     float mx = -INFINITY, sm = 0.f;
                     const int gl = (tlen + 15) >> 4;
                     for (int g = 0; g < gl; ++g) {
@@ -606,25 +716,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                         uint32_t r[16];
                         tmem_ld16(tcol + (uint32_t)(16 * g), r);
                         float d[16], gm = -INFINITY;
-                        if (16 * g + 16 <= tlen) {
+                        const int nv = tlen - 16 * g;                              // >= 1
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) { d[j] = fmaf(__uint_as_float(r[j]), ss[j], cc[j]); gm = fmaxf(gm, d[j]); }
-                        } else {
-                            const int nv = tlen - 16 * g;                          // >= 1
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) { d[j] = (j < nv) ? fmaf(__uint_as_float(r[j]), ss[j], cc[j]) : -INFINITY; gm = fmaxf(gm, d[j]); }
-                        }
+                        for (int j = 0; j < 16; ++j) { d[j] = (j < nv) ? fmaf(__uint_as_float(r[j]), ss[j], cc[j]) : -INFINITY; gm = fmaxf(gm, d[j]); }
                         const float nm = fmaxf(mx, gm);
                         const float nml = nm * L2E;
-                        float part = 0.f;
+                        float psum = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) part += fast_exp2(fmaf(d[j], L2E, -nml));   // 2^-inf = 0 for the padding
-                        sm = fmaf(sm, fast_exp2((mx - nm) * L2E), part);
+                        for (int j = 0; j < 16; ++j) psum += fast_exp2(fmaf(d[j], L2E, -nml));
+                        sm = fmaf(sm, fast_exp2((mx - nm) * L2E), psum);
                         mx = nm;
                     }
                     const float lse = mx + fast_log2(sm) * LN2;
                     float* o = ob;
-                    if (p.prior_scaling > 0.f) {
+                    {
                         // Beta-binomial alignment prior of the OTA paper, generated here instead of read from a [b, t_x, t_y] tensor:
                         //   prior[x, y] = BetaBinom(x; n = t_x - 1, a = s (y + 1), b = s (t_y - y))        (oracle/neg_cent.py:beta_binomial_prior)
                         // This thread owns frame y and walks the tokens in order, so the pmf is a recurrence along x,
@@ -662,32 +767,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                                 }
                             }
                         }
-                    } else
-                    for (int g = 0; g < ngroups; ++g) {
-                        NC_LOAD_TERMS(g)
-                        uint32_t r[16];
-                        tmem_ld16(tcol + (uint32_t)(16 * g), r);
-                        if (y_ok) {
-                            if (16 * g + 16 <= tlen && pr == nullptr) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) { *o = fmaf(__uint_as_float(r[j]), ss[j], cc[j]) - lse; o += Ty; }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const int xl = 16 * g + j;
-                                    if (xl < Tx) {
-                                        float v = -INFINITY;        // text padding is excluded from the softmax
-                                        if (xl < tlen) {
-                                            v = fmaf(__uint_as_float(r[j]), ss[j], cc[j]) - lse;
-                                            if (pr) v += __logf(pr[(size_t)xl * Ty] + 1e-8f);
-                                        }
-                                        *o = v; o += Ty;
-                                    }
-                                }
-                            }
-                        }
                     }
-                } else if (y_ok) {
+                } else {
+                  if (helpers) asm volatile("bar.sync 2, 384;" ::: "memory");   // the helpers skip an exact tile; keep the barrier count
+                  if (y_ok) {
                     // exact fp32 from the raw inputs: squared distance from differences, two passes over the text axis
                     const float T = p.temperature;
                     const float* qb = p.a_src + (size_t)b * p.C * Ty + y;
@@ -723,6 +806,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                             }
                         }
                     }
+                  }
                 }
             }
 #undef NC_LOAD_TERMS
@@ -730,7 +814,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
             mbar_arrive(bar_t_empty + 8 * slot);               // 128 arrivals: the accumulator may be overwritten
             if (wid == 11 && lane == 0) NC_STAMP(4, it, 2);
             if (p.ready != nullptr) __threadfence();          // this thread's part of the tile is visible device-wide ...
-            asm volatile("bar.sync 1, 128;" ::: "memory");    // every epilogue thread is done with this tile's per-token terms
+            if (helpers) asm volatile("bar.sync 2, 384;" ::: "memory");
+            else asm volatile("bar.sync 1, 128;" ::: "memory");    // every epilogue thread is done with this tile's per-token terms
             if (p.ready != nullptr && wid == 11 && lane == 0)   // ... before the tile is published to the search running beside us
                 asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.ready + (size_t)b * p.n_mtiles + mt), "r"(p.epoch) : "memory");
         }
