@@ -275,6 +275,7 @@ struct V2Params {
     int npass, nchunks, n_mtiles, n_items;
     int sr;                    // raw stages
     uint32_t off_a, off_b, off_aux, b_stage_bytes;   // raw ring at offset 0
+    int sb;                    // text-operand stages: 2, or 1 for texts longer than 256 tokens (a stage then holds both token blocks)
 };
 
 __device__ __forceinline__ void item_to_tile(const V2Params& p, int item, int& b, int& mt) {
@@ -362,9 +363,12 @@ __device__ __forceinline__ void ota_fast_part(uint32_t tcol, const float4* colv4
 #undef NC_LOAD_TERMS2
 }
 
-template <int MODE>
+// BB: OTA with the beta-binomial prior generated in the epilogue -- its own instance, so that the fp64 lgamma code does not weigh on
+// the registers of the plain OTA kernel
+template <int MODE, bool BB = false>
 __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, const __grid_constant__ CUtensorMap map_a,
-                                                            const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo)
+                                                            const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                                                            const __grid_constant__ CUtensorMap map_bhi2, const __grid_constant__ CUtensorMap map_blo2)
 {
     constexpr int RPC = MODE == 0 ? 1 : 2;                   // raw boxes per 64-k chunk (gaussian: 2 k per channel)
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -372,10 +376,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
     const uint32_t base = smem_u32(smem);
     const uint32_t raw0 = base, a0 = base + p.off_a, b0 = base + p.off_b, aux = base + p.off_aux;
     // aux: barriers (8 bytes each), then the tmem slot, then per-tile flags and |q|^2 rows
-    const uint32_t bar_raw_full = aux, bar_raw_empty = aux + 32, bar_a_full = aux + 64, bar_b_full = aux + 80, bar_ab_empty = aux + 96,
-                   bar_t_full = aux + 112, bar_t_empty = aux + 128, tmem_slot = aux + 144;
+    const uint32_t bar_raw_full = aux, bar_raw_empty = aux + 32, bar_a_full = aux + 64, bar_b_full = aux + 80, bar_a_empty = aux + 96,
+                   bar_t_full = aux + 112, bar_t_empty = aux + 128, tmem_slot = aux + 144, bar_b_empty = aux + 192;
     volatile int* ovf = reinterpret_cast<volatile int*>(smem + p.off_aux + 160);          // [8] per-tile "mel side out of fp16 range"
     const int SR = p.sr;
+    const uint32_t SB = (uint32_t)p.sb;
 
     if ((base & 1023u) != 0u) __trap();                      // the swizzle atoms need 1024-byte alignment
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a search launched behind us may start beside us (it polls p.ready)
@@ -389,8 +394,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
     }
     if (tid == 0) {
         for (int s = 0; s < 4; ++s) { mbar_init(bar_raw_full + 8 * s, 1); mbar_init(bar_raw_empty + 8 * s, N_TRANSFORM / 32); }
-        for (int s = 0; s < SA; ++s) { mbar_init(bar_a_full + 8 * s, N_TRANSFORM); mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_ab_empty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, (MODE == 1 && p.npass > 1 && !(p.prior_scaling > 0.f)) ? 384 : 128); }
+        for (int s = 0; s < SA; ++s) { mbar_init(bar_a_full + 8 * s, N_TRANSFORM); mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_a_empty + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, (MODE == 1 && p.npass > 1 && !BB) ? 384 : 128); }
         for (int s = 0; s < 8; ++s) ovf[s] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -404,7 +409,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
     const int two_slots = (p.npass == 1);
     // OTA with a text longer than 256 tokens: one accumulator spanning both TMEM halves, so the epilogue overlaps nothing and the
     // eight transform warps (idle by then) take two thirds of it (not with the generated prior: its recurrence walks every token)
-    const bool helpers = (MODE == 1) && !two_slots && !(p.prior_scaling > 0.f);
+    const bool helpers = (MODE == 1) && !two_slots && !BB;
     float* xch = reinterpret_cast<float*>(smem + p.off_aux + 256 + 2 * 512 * 4);
 
     if (wid == 0) {
@@ -415,7 +420,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                 int b, mt;
                 item_to_tile(p, item, b, mt);
                 const int y0 = mt * BM;
-                for (int pass = 0; pass < p.npass; ++pass)
+                // (a text longer than 256 tokens is two token blocks of the SAME mel-side operand: it is loaded and converted once)
                     for (int ch = 0; ch < p.nchunks * RPC; ++ch, ++rc) {
                         const uint32_t rs = rc % SR, rph = (rc / SR) & 1u;
                         NC_STAMP(0, rc, 0);
@@ -436,16 +441,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int b, mt;
                 item_to_tile(p, item, b, mt);
-                for (int pass = 0; pass < p.npass; ++pass)
                     for (int ch = 0; ch < p.nchunks; ++ch, ++cc) {
-                        const uint32_t s = cc % SA, ph = (cc / SA) & 1u;
+                        const uint32_t s = cc % SB, ph = (cc / SB) & 1u;
                         NC_STAMP(1, cc, 0);
-                        mbar_wait(bar_ab_empty + 8 * s, ph ^ 1u);
+                        mbar_wait(bar_b_empty + 8 * s, ph ^ 1u);
                         NC_STAMP(1, cc, 1);
-                        mbar_expect_tx(bar_b_full + 8 * s, 2u * (uint32_t)p.NB * 128u);
-                        const uint32_t bs = b0 + s * p.b_stage_bytes;
-                        tma_load_3d(bs, &map_bhi, ch * KC, pass * 256, b, bar_b_full + 8 * s);
-                        tma_load_3d(bs + (uint32_t)p.NB * 128u, &map_blo, ch * KC, pass * 256, b, bar_b_full + 8 * s);
+                        mbar_expect_tx(bar_b_full + 8 * s, 2u * (uint32_t)p.NT * 128u);
+                        // stage layout: hi rows [0, NB) | hi rows [256, NT) | lo rows [0, NB) | lo rows [256, NT)
+                        const uint32_t bs = b0 + s * p.b_stage_bytes, lo = (uint32_t)p.NT * 128u;
+                        tma_load_3d(bs, &map_bhi, ch * KC, 0, b, bar_b_full + 8 * s);
+                        tma_load_3d(bs + lo, &map_blo, ch * KC, 0, b, bar_b_full + 8 * s);
+                        if (p.npass > 1) {
+                            tma_load_3d(bs + 256u * 128u, &map_bhi2, ch * KC, 256, b, bar_b_full + 8 * s);
+                            tma_load_3d(bs + lo + 256u * 128u, &map_blo2, ch * KC, 256, b, bar_b_full + 8 * s);
+                        }
                     }
             }
         }
@@ -458,44 +467,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                 const uint32_t slot = two_slots ? (it & 1u) : 0u, use = two_slots ? (it >> 1) : it;
                 mbar_wait(bar_t_empty + 8 * slot, (use & 1u) ^ 1u);          // the epilogue has drained this accumulator
                 fence_after();
-                for (int pass = 0; pass < p.npass; ++pass) {
-                    const int ncols = min(256, p.NT - pass * 256);
-                    const uint32_t idesc = make_idesc(ncols);
-                    const uint32_t dcol = tmem_base + slot * 256u + (uint32_t)pass * 256u;
-                    for (int ch = 0; ch < p.nchunks; ++ch, ++cc) {
-                        const uint32_t s = cc % SA, ph = (cc / SA) & 1u;
-                        NC_STAMP(2, cc, 0);
-                        if (!ready) {                                               // (normally already waited for, see below)
-                            mbar_wait(bar_a_full + 8 * s, ph);
-                            NC_STAMP(2, cc, 1);
-                            mbar_wait(bar_b_full + 8 * s, ph);
-                        }
-                        ready = false;
-                        NC_STAMP(2, cc, 2);
-                        fence_after();
-                        const uint32_t sA_hi = a0 + s * 2u * A_TILE, sA_lo = sA_hi + A_TILE;
-                        const uint32_t sB_hi = b0 + s * p.b_stage_bytes, sB_lo = sB_hi + (uint32_t)p.NB * 128u;
-                        const int nk = min(4, (K - ch * KC + 15) >> 4);             // 16-k steps that hold real channels
+                for (int ch = 0; ch < p.nchunks; ++ch, ++cc) {
+                    const uint32_t s = cc % SA, ph = (cc / SA) & 1u, sbs = cc % SB, bph = (cc / SB) & 1u;
+                    NC_STAMP(2, cc, 0);
+                    if (!ready) {                                                   // (normally already waited for, see below)
+                        mbar_wait(bar_a_full + 8 * s, ph);
+                        NC_STAMP(2, cc, 1);
+                        mbar_wait(bar_b_full + 8 * sbs, bph);
+                    }
+                    ready = false;
+                    NC_STAMP(2, cc, 2);
+                    fence_after();
+                    const uint32_t sA_hi = a0 + s * 2u * A_TILE, sA_lo = sA_hi + A_TILE;
+                    const int nk = min(4, (K - ch * KC + 15) >> 4);                 // 16-k steps that hold real channels
+                    // a text longer than 256 tokens: two token blocks = two MMA series into the two TMEM halves, same A stage
+                    for (int pass = 0; pass < p.npass; ++pass) {
+                        const int ncols = min(256, p.NT - pass * 256);
+                        const uint32_t idesc = make_idesc(ncols);
+                        const uint32_t dcol = tmem_base + slot * 256u + (uint32_t)pass * 256u;
+                        const uint32_t sB_hi = b0 + sbs * p.b_stage_bytes + (uint32_t)pass * (256u * 128u), sB_lo = sB_hi + (uint32_t)p.NT * 128u;
 #pragma unroll
                         for (int prod = 0; prod < 3; ++prod) {
                             const uint32_t sa = (prod == 1) ? sA_lo : sA_hi;         // hi*hi, lo*hi, hi*lo
                             const uint32_t sb = (prod == 2) ? sB_lo : sB_hi;
 #ifndef NC_NO_LOOKAHEAD
-                            if (prod == 2 && !(pass == p.npass - 1 && ch == p.nchunks - 1)) {
+                            if (prod == 2 && pass == p.npass - 1 && ch != p.nchunks - 1 && SB > 1) {
                                 // the tensor pipe still has this chunk's first two products queued: the barrier round trips of the
                                 // NEXT chunk (same tile) hide behind them instead of opening a gap between the chunks
                                 const uint32_t s2 = (cc + 1) % SA, ph2 = ((cc + 1) / SA) & 1u;
                                 mbar_wait(bar_a_full + 8 * s2, ph2);
-                                mbar_wait(bar_b_full + 8 * s2, ph2);
+                                mbar_wait(bar_b_full + 8 * ((cc + 1) % SB), ((cc + 1) / SB) & 1u);
                                 ready = true;
                             }
 #endif
                             for (int ks = 0; ks < nk; ++ks)                          // 16 fp16 = 32 bytes along the swizzled row
                                 mma_f16(dcol, make_desc(sa + ks * 32), make_desc(sb + ks * 32), idesc, (ch | prod | ks) ? 1u : 0u);
                         }
-                        mma_commit(bar_ab_empty + 8 * s);                           // stage reusable when these MMAs have read it
-                        NC_STAMP(2, cc, 3);
                     }
+                    mma_commit(bar_a_empty + 8 * s);                                // both stages reusable when these MMAs have read them
+                    mma_commit(bar_b_empty + 8 * sbs);
+                    NC_STAMP(2, cc, 3);
                 }
                 mma_commit(bar_t_full + 8 * slot);                                  // accumulator complete
             }
@@ -509,7 +520,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
         // the tensor core: what remains on the critical path after "stage free" is eight stores, a proxy fence and an arrival.
         uint32_t rc = 0, cc = 0, it = 0;
         uint32_t H[RPC * (MODE == 0 ? 4 : 2)][4], L[RPC * (MODE == 0 ? 4 : 2)][4];
-        const uint32_t total_chunks = (uint32_t)p.npass * (uint32_t)p.nchunks;
+        const uint32_t total_chunks = (uint32_t)p.nchunks;          // (the mel-side operand of a tile is produced once, whatever the text length)
         bool bad = false;
         auto produce = [&]() {                               // raw boxes of the next chunk -> H / L
 #pragma unroll
@@ -555,7 +566,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
             for (uint32_t ci = 0; ci < total_chunks; ++ci, ++cc) {
                 const uint32_t s = cc % SA, ph = (cc / SA) & 1u;
                 const uint32_t sA_hi = a0 + s * 2u * A_TILE + a_row, sA_lo = sA_hi + A_TILE;
-                mbar_wait(bar_ab_empty + 8 * s, ph ^ 1u);
+                mbar_wait(bar_a_empty + 8 * s, ph ^ 1u);
                 if (t == 0) NC_STAMP(3, cc, 2);
                 if (MODE == 0) {
 #pragma unroll
@@ -705,7 +716,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                 const int tlen = p.x_lengths ? min(max(p.x_lengths[b], 0), Tx) : Tx;
                 const float* pr = p.prior ? p.prior + (size_t)b * Tx * Ty + (y_ok ? y : 0) : nullptr;
                 constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-                if (!slow && !(p.prior_scaling > 0.f)) {
+                if (!slow && !BB) {
                     ota_fast_part(tcol, colv4, isb4, xch, helpers ? 2 : 0, helpers ? 3 : 1, row, y_ok, Tx, Ty, p.NT, tlen, pr, ob);
                 } else if (!slow) {
                     // generated beta-binomial prior: this thread walks every token in order
@@ -790,7 +801,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                                 if (x < tlen) {
                                     v -= lse;
                                     if (pr) v += logf(pr[(size_t)x * Ty] + 1e-8f);
-                                    if (p.prior_scaling > 0.f) {                     // generated prior, straight from the definition (exact path: speed is irrelevant)
+                                    if (BB) {                                        // generated prior, straight from the definition (exact path: speed is irrelevant)
                                         const int tyl = p.y_lengths ? min(max(p.y_lengths[b], 0), Ty) : Ty;
                                         const int n = tlen - 1;
                                         double pm = 0.0;
@@ -836,7 +847,7 @@ static int fail(int code, const char* who, const char* msg)
     return code;
 }
 
-struct Plan { int K, Kpad, NT, NB, npass, nchunks, sr; uint32_t off_a, off_b, off_aux, b_stage, smem; size_t ws_bhi, ws_blo, ws_colv, ws_isb, ws_total; };
+struct Plan { int K, Kpad, NT, NB, npass, nchunks, sr, sb; uint32_t off_a, off_b, off_aux, b_stage, smem; size_t ws_bhi, ws_blo, ws_colv, ws_isb, ws_total; };
 
 static bool make_plan(int mode, int b, int c, int tx, int ty, Plan* pl)
 {
@@ -847,16 +858,17 @@ static bool make_plan(int mode, int b, int c, int tx, int ty, Plan* pl)
     pl->NB = pl->NT < 256 ? pl->NT : 256;
     pl->npass = (pl->NT + 255) / 256;
     pl->nchunks = pl->Kpad / KC;
-    pl->b_stage = 2u * pl->NB * 128u;
+    pl->b_stage = 2u * pl->NT * 128u;                    // hi + lo, every token row of the tile (both 256-token blocks of a long text)
+    pl->sb = pl->npass == 1 ? SA : 1;
     // raw ring first (16 KB stages keep everything after it 1024-byte aligned), then A, then B, then aux
-    const int budget = 232448 - AUX_BYTES - SA * 2 * A_TILE - SA * (int)pl->b_stage;
+    const int budget = 232448 - AUX_BYTES - SA * 2 * A_TILE - pl->sb * (int)pl->b_stage;
     int sr = budget / RAW_BYTES;
     if (sr > 4) sr = 4;
     if (sr < 1) return false;                 // (one stage is enough to run: the transform warps hold the next chunk in registers)
     pl->sr = sr;
     pl->off_a = sr * RAW_BYTES;
     pl->off_b = pl->off_a + SA * 2 * A_TILE;
-    pl->off_aux = pl->off_b + SA * pl->b_stage;
+    pl->off_aux = pl->off_b + pl->sb * pl->b_stage;
     pl->smem = pl->off_aux + AUX_BYTES;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     pl->ws_bhi = 0;
@@ -897,7 +909,8 @@ static int run(const float* a_src, const float* b_src0, const float* b_src1, con
     if (dev < 0 || dev >= 64) return ALB200_E_UNSUPPORTED;
     if (!configured[dev]) {
         cudaError_t e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(nc_v2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nc_v2_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e == cudaSuccess && MODE == 1) e = cudaFuncSetAttribute(nc_v2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nc_prep_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return fail(ALB200_E_CUDA, who, cudaGetErrorString(e));
         configured[dev] = true;
@@ -912,17 +925,20 @@ static int run(const float* a_src, const float* b_src0, const float* b_src1, con
     if (prep_smem > 200 * 1024) return ALB200_E_UNSUPPORTED;
     nc_prep_kernel<MODE><<<dim3((tx + PT - 1) / PT, b), 256, prep_smem, stream>>>(b_src0, b_src1, b_hi, b_lo, colv, isb, c, tx, pl.K, pl.Kpad, pl.NT, temperature);
     ++alb::g_launches;
-    CUtensorMap map_a, map_bhi, map_blo;
+    CUtensorMap map_a, map_bhi, map_blo, map_bhi2, map_blo2;
     int rc = encode3(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_src, (uint64_t)ty, (uint64_t)c, (uint64_t)b, BM, RAW_CH, CU_TENSOR_MAP_SWIZZLE_NONE, who);
     if (!rc) rc = encode3(&map_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_hi, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, (uint32_t)pl.NB, CU_TENSOR_MAP_SWIZZLE_128B, who);
     if (!rc) rc = encode3(&map_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_lo, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, (uint32_t)pl.NB, CU_TENSOR_MAP_SWIZZLE_128B, who);
+    const uint32_t rows2 = pl.npass > 1 ? (uint32_t)(pl.NT - 256) : (uint32_t)pl.NB;        // second token block of a long text
+    if (!rc) rc = encode3(&map_bhi2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_hi, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, rows2, CU_TENSOR_MAP_SWIZZLE_128B, who);
+    if (!rc) rc = encode3(&map_blo2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_lo, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, rows2, CU_TENSOR_MAP_SWIZZLE_128B, who);
     if (rc) return rc;
     V2Params p;
     memset(&p, 0, sizeof(p));
     p.a_src = a_src; p.b_src0 = b_src0; p.b_src1 = b_src1; p.colv = colv; p.inv_sb = isb; p.prior = prior; p.x_lengths = x_lengths; p.out = out;
     p.temperature = temperature; p.B = b; p.C = c; p.Tx = tx; p.Ty = ty; p.NT = pl.NT; p.NB = pl.NB; p.npass = pl.npass; p.nchunks = pl.nchunks;
     p.n_mtiles = (ty + BM - 1) / BM; p.n_items = b * p.n_mtiles; p.sr = pl.sr;
-    p.off_a = pl.off_a; p.off_b = pl.off_b; p.off_aux = pl.off_aux; p.b_stage_bytes = pl.b_stage;
+    p.off_a = pl.off_a; p.off_b = pl.off_b; p.off_aux = pl.off_aux; p.b_stage_bytes = pl.b_stage; p.sb = pl.sb;
     p.ready = ready; p.epoch = epoch; p.tile_major = ready != nullptr;
     p.y_lengths = y_lengths; p.prior_scaling = prior_scaling;
     int grid = p.n_items < sms ? p.n_items : sms;
@@ -944,7 +960,8 @@ static int run(const float* a_src, const float* b_src0, const float* b_src1, con
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = at; lc.numAttrs = alb::opts().nc_no_pdl ? 0 : 1;
-        cudaError_t le = cudaLaunchKernelEx(&lc, nc_v2_kernel<MODE>, p, map_a, map_bhi, map_blo);
+        cudaError_t le = (MODE == 1 && prior_scaling > 0.f) ? cudaLaunchKernelEx(&lc, nc_v2_kernel<1, true>, p, map_a, map_bhi, map_blo, map_bhi2, map_blo2)
+                                                             : cudaLaunchKernelEx(&lc, nc_v2_kernel<MODE, false>, p, map_a, map_bhi, map_blo, map_bhi2, map_blo2);
         if (le != cudaSuccess) return fail(ALB200_E_CUDA, who, cudaGetErrorString(le));
     }
     ++alb::g_launches;
