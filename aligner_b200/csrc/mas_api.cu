@@ -365,7 +365,7 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
                       int64_t msb, int64_t msx, int64_t msy, void* paths, int esize, uint64_t one, int zero_fill,
                       int32_t* frame_tok, int32_t* durations, int32_t* lens_out, int b, int tx, int ty, float neg,
                       void* workspace, size_t workspace_bytes, cudaStream_t stream, int vt = 0, int vl = 0,
-                      const int* tile_ready = nullptr, int ready_epoch = 0, int ready_tiles = 0)
+                      const int* tile_ready = nullptr, int ready_epoch = 0, int ready_tiles = 0, int pdl_wait = 0)
 {
     if (!values || b < 0 || tx <= 0 || ty <= 0) return fail(ALB200_E_INVALID, "null values or non-positive shape%s", "");
     if (!mask && (!t_xs || !t_ys)) return fail(ALB200_E_INVALID, "need lengths or a mask%s", "");
@@ -420,7 +420,7 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
         }
     }
     p.neg = neg;
-    p.tile_ready = tile_ready; p.ready_epoch = ready_epoch; p.ready_tiles = ready_tiles;
+    p.tile_ready = tile_ready; p.ready_epoch = ready_epoch; p.ready_tiles = ready_tiles; p.pdl_wait = pdl_wait;
     static long long* d_dbg = nullptr;
     const bool dbg = kDbgBuild && opts().dbg == 1;
     const size_t dbg_n = (size_t)c.grid * ((2 * kMaxWarps + 2) * 2 + kMaxWarps * 8);
@@ -431,7 +431,7 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
         p.dbg = d_dbg;
     }
     void* args[] = { &p, &tmap, &tmap_tail };
-    if (c.nc > 1 || tile_ready != nullptr) {
+    if (c.nc > 1 || tile_ready != nullptr || pdl_wait) {
         cudaLaunchConfig_t lc;
         memset(&lc, 0, sizeof(lc));
         lc.gridDim = dim3(c.grid); lc.blockDim = dim3(2 * c.NW * 32); lc.dynamicSmemBytes = c.smem; lc.stream = stream;
@@ -442,9 +442,11 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
             at[na].val.clusterDim.x = c.nc; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
             ++na;
         }
-        if (tile_ready != nullptr) {
-            // pipelined with the score kernel launched just before on this stream: start beside it (it signals at its start and
-            // has left SMs free); the loader warps poll tile_ready, nothing here waits for that kernel as a whole
+        if (tile_ready != nullptr || pdl_wait) {
+            // launched programmatically dependent on the score kernel just before on this stream (it signals at its start).
+            // Pipelined form: starts beside it on the SMs it left free, the loader warps poll tile_ready, nothing waits for that
+            // kernel as a whole.  Back-to-back form (pdl_wait): CTAs start as SMs drain, set up, start the zero fill, and the
+            // loaders execute griddepcontrol.wait before the first score load.
             at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[na].val.programmaticStreamSerializationAllowed = 1;
             ++na;
@@ -651,7 +653,9 @@ int alb200_gaussian_mas_fused(const float* z, const float* m_p, const float* log
     const int free_sms = di.sms - cfg.grid;
     const int fmode = opts().fused_seq;                       // tuning: 1 = always back to back, 2 = pipelined whenever possible
     const bool can_pipe = nc_bytes > 0 && is_latency(di, b, tx, ty, aligned, 0) && cfg.grid <= di.sms && free_sms >= 32 && !opts().nc_ffma && !opts().nc_v1;
-    const bool pipelined = can_pipe && fmode != 1 && (fmode == 2 || cfg.grid * 3 <= di.sms);
+    // ... and only when the score kernel has at least two rounds of tiles on the SMs left to it: with a single round every tile is
+    // finished at about the same time and there is nothing to overlap (16 x 100 x 800: 47 us pipelined, 45 back to back)
+    const bool pipelined = can_pipe && fmode != 1 && (fmode == 2 || (cfg.grid * 3 <= di.sms && (int64_t)b * n_mt >= 2 * (int64_t)free_sms));
     if (pipelined) {
         ALB_CUDA(cudaMemsetAsync(flags, 0, (size_t)b * n_mt * 4, stream));
         if (kDbgBuild && opts().dbg == 2) {      // developer aid: global-timer stamps of both kernels (see the kernels)
@@ -675,8 +679,11 @@ int alb200_gaussian_mas_fused(const float* z, const float* m_p, const float* log
     }
     rc = alb200_neg_cent_gaussian_ws(z, m_p, logs_p, neg_cent, b, c, tx, ty, nc_bytes ? ws : nullptr, nc_bytes, stream);
     if (rc) return rc;
+    // back to back, but still programmatically dependent when the TMA / tcgen05 score kernel ran (it signals its dependents):
+    // the search's launch, set-up and the start of its zero fill hide under the score kernel's tail
+    const int pdl = (nc_bytes > 0 && !opts().nc_ffma && !opts().nc_v1 && !opts().nc_no_pdl) ? 1 : 0;
     return launch_mas(neg_cent, t_xs, t_ys, mask, mask_dtype, msb, msx, msy, paths, path_elem_size, path_one, zero_fill, frame_tok, durations,
-                      nullptr, b, tx, ty, max_neg_val, mas_ws, mas_ws_bytes, stream);
+                      nullptr, b, tx, ty, max_neg_val, mas_ws, mas_ws_bytes, stream, 0, 0, nullptr, 0, 0, pdl);
 }
 
 int alb200_mas_status(void* workspace, void* stream)

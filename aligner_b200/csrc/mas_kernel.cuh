@@ -89,6 +89,8 @@ struct MasParams {
     // tile_ready[item * ready_tiles + k] == ready_epoch once frames [128 k, 128 k + 128) of every token row of `item` are in global memory.
     const int* tile_ready;
     int ready_epoch, ready_tiles;
+    int pdl_wait;               // launched programmatically dependent on the kernel that writes `values` (fused entry, back-to-back form):
+                                // everything up to the first score load overlaps that kernel's tail, the loaders then wait for it
     uint64_t one;
     int64_t bits_slot_words;
     int B, Tx, Ty;
@@ -797,6 +799,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 const int zq = (int)((my_chunks + my_tiles - 1) / (my_tiles > 0 ? my_tiles : 1));
                 long long l_e = 0, l_c = 0, l_z = 0, l0 = 0, l1 = 0, l2 = 0;
                 int known_ready = -1;                               // highest producer tile known to be published (pipelined mode)
+                if (p.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // the scores are complete and visible from here on
                 for (int t = t_s; t < t_e; ++t) {
                     if (dbg_on) l0 = clock64();
                     mbar_wait(empty0 + 8 * stage, phase ^ 1u);      // the compute lanes have released this stage

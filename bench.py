@@ -379,7 +379,7 @@ def bench_neg_cent(torch, dev, timer, ma, lib, peak_tflops):
                           "peak_bf16_tflops_measured": peak_tflops,
                           "pipeline_neg_cent_plus_mas_us": pms * 1e3,
                           "fused_entry_us": fms * 1e3, "fused_entry_launches": flaunches // 20 if flaunches else None,
-                          "fused_entry_mode": "back to back (64 utterances need 64 of 148 SMs: pipelining measured no gain, DESIGN.md)",
+                          "fused_entry_mode": "back to back, the search launched programmatically dependent on the score kernel (64 utterances need 64 of 148 SMs: pipelining measured no gain, DESIGN.md)",
                           "fused_bit_identical_to_separate_calls": fused_ok}
     # ---- the pipelined form of the fused entry pays when the search needs at most a third of the SMs: C3's shape with the Gaussian score
     b3, tx3, ty3 = 32, 300, 1500
