@@ -104,6 +104,13 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, accumulating unconditionally (the predicate folds to PT: no SETP on the issuing thread's critical path)
+__device__ __forceinline__ void mma_f16_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -486,22 +493,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                         const uint32_t idesc = make_idesc(ncols);
                         const uint32_t dcol = tmem_base + slot * 256u + (uint32_t)pass * 256u;
                         const uint32_t sB_hi = b0 + sbs * p.b_stage_bytes + (uint32_t)pass * (256u * 128u), sB_lo = sB_hi + (uint32_t)p.NT * 128u;
-#pragma unroll
-                        for (int prod = 0; prod < 3; ++prod) {
-                            const uint32_t sa = (prod == 1) ? sA_lo : sA_hi;         // hi*hi, lo*hi, hi*lo
-                            const uint32_t sb = (prod == 2) ? sB_lo : sB_hi;
+                        // The single issuing thread is on the critical path (12 MMAs of ~110 cycles each per chunk): descriptors are
+                        // formed once per chunk, a k-step is "+2" on the 16-byte-unit address field, and the common case (four
+                        // k-steps) is straight-line code.
+                        const uint64_t dAh = make_desc(sA_hi), dAl = make_desc(sA_lo), dBh = make_desc(sB_hi), dBl = make_desc(sB_lo);
+                        if (nk == 4) {
+                            mma_f16(dcol, dAh, dBh, idesc, ch ? 1u : 0u);                                  // hi * hi
+                            mma_f16_acc(dcol, dAh + 2, dBh + 2, idesc); mma_f16_acc(dcol, dAh + 4, dBh + 4, idesc); mma_f16_acc(dcol, dAh + 6, dBh + 6, idesc);
+                            mma_f16_acc(dcol, dAl, dBh, idesc); mma_f16_acc(dcol, dAl + 2, dBh + 2, idesc);  // lo * hi
+                            mma_f16_acc(dcol, dAl + 4, dBh + 4, idesc); mma_f16_acc(dcol, dAl + 6, dBh + 6, idesc);
+                        } else {
+                            for (int ks = 0; ks < nk; ++ks) mma_f16(dcol, dAh + 2 * ks, dBh + 2 * ks, idesc, (ch | ks) ? 1u : 0u);
+                            for (int ks = 0; ks < nk; ++ks) mma_f16_acc(dcol, dAl + 2 * ks, dBh + 2 * ks, idesc);
+                        }
 #ifndef NC_NO_LOOKAHEAD
-                            if (prod == 2 && pass == p.npass - 1 && ch != p.nchunks - 1 && SB > 1) {
-                                // the tensor pipe still has this chunk's first two products queued: the barrier round trips of the
-                                // NEXT chunk (same tile) hide behind them instead of opening a gap between the chunks
-                                const uint32_t s2 = (cc + 1) % SA, ph2 = ((cc + 1) / SA) & 1u;
-                                mbar_wait(bar_a_full + 8 * s2, ph2);
-                                mbar_wait(bar_b_full + 8 * ((cc + 1) % SB), ((cc + 1) / SB) & 1u);
-                                ready = true;
-                            }
+                        if (pass == p.npass - 1 && ch != p.nchunks - 1 && SB > 1) {
+                            // the tensor pipe still has this chunk's first two products queued: the barrier round trips of the
+                            // NEXT chunk (same tile) hide behind them instead of opening a gap between the chunks
+                            const uint32_t s2 = (cc + 1) % SA, ph2 = ((cc + 1) / SA) & 1u;
+                            mbar_wait(bar_a_full + 8 * s2, ph2);
+                            mbar_wait(bar_b_full + 8 * ((cc + 1) % SB), ((cc + 1) / SB) & 1u);
+                            ready = true;
+                        }
 #endif
-                            for (int ks = 0; ks < nk; ++ks)                          // 16 fp16 = 32 bytes along the swizzled row
-                                mma_f16(dcol, make_desc(sa + ks * 32), make_desc(sb + ks * 32), idesc, (ch | prod | ks) ? 1u : 0u);
+                        if (nk == 4) {                                                                     // hi * lo
+                            mma_f16_acc(dcol, dAh, dBl, idesc); mma_f16_acc(dcol, dAh + 2, dBl + 2, idesc);
+                            mma_f16_acc(dcol, dAh + 4, dBl + 4, idesc); mma_f16_acc(dcol, dAh + 6, dBl + 6, idesc);
+                        } else {
+                            for (int ks = 0; ks < nk; ++ks) mma_f16_acc(dcol, dAh + 2 * ks, dBl + 2 * ks, idesc);
                         }
                     }
                     mma_commit(bar_a_empty + 8 * s);                                // both stages reusable when these MMAs have read them
@@ -893,6 +912,29 @@ static int encode3(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void
     return 0;
 }
 
+// cuTensorMapEncodeTiled costs 1-2 us of host time each and the score call needs up to five: the last few are remembered per
+// thread (same pointer, shape and box -> same map), and all of them are encoded BEFORE the prep kernel is launched so that the
+// two launches of a call go out back to back.
+static int encode3_cached(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                          CUtensorMapSwizzle sw, const char* who)
+{
+    struct Key { const void* ptr; uint64_t d0, d1, d2; uint32_t b0, b1; int dt, sw; };
+    static thread_local Key keys[32];
+    static thread_local CUtensorMap maps[32];
+    static thread_local int used = 0, next = 0;
+    const Key k = { ptr, d0, d1, d2, b0, b1, (int)dt, (int)sw };
+    for (int i = 0; i < used; ++i)
+        if (keys[i].ptr == k.ptr && keys[i].d0 == d0 && keys[i].d1 == d1 && keys[i].d2 == d2 && keys[i].b0 == b0 && keys[i].b1 == b1 && keys[i].dt == k.dt && keys[i].sw == k.sw) {
+            *m = maps[i];
+            return 0;
+        }
+    const int rc = encode3(m, dt, esize, ptr, d0, d1, d2, b0, b1, sw, who);
+    if (rc) return rc;
+    keys[next] = k; maps[next] = *m;
+    next = (next + 1) % 32; if (used < 32) ++used;
+    return 0;
+}
+
 template <int MODE>
 static int run(const float* a_src, const float* b_src0, const float* b_src1, const float* prior, const int32_t* x_lengths, float* out, float temperature,
                int b, int c, int tx, int ty, void* workspace, size_t workspace_bytes, cudaStream_t stream, const char* who,
@@ -923,16 +965,19 @@ static int run(const float* a_src, const float* b_src0, const float* b_src1, con
     float* isb = reinterpret_cast<float*>(ws + pl.ws_isb);
     const size_t prep_smem = (size_t)PT * (pl.Kpad + 4) * 4;
     if (prep_smem > 200 * 1024) return ALB200_E_UNSUPPORTED;
+    CUtensorMap map_a, map_bhi, map_blo, map_bhi2, map_blo2;
+    int rc = encode3_cached(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_src, (uint64_t)ty, (uint64_t)c, (uint64_t)b, BM, RAW_CH, CU_TENSOR_MAP_SWIZZLE_NONE, who);
+    if (!rc) rc = encode3_cached(&map_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_hi, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, (uint32_t)pl.NB, CU_TENSOR_MAP_SWIZZLE_128B, who);
+    if (!rc) rc = encode3_cached(&map_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_lo, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, (uint32_t)pl.NB, CU_TENSOR_MAP_SWIZZLE_128B, who);
+    map_bhi2 = map_bhi; map_blo2 = map_blo;                   // (one token block: never dereferenced)
+    if (pl.npass > 1) {                                        // second token block of a long text: its own, shorter box
+        const uint32_t rows2 = (uint32_t)(pl.NT - 256);
+        if (!rc) rc = encode3_cached(&map_bhi2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_hi, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, rows2, CU_TENSOR_MAP_SWIZZLE_128B, who);
+        if (!rc) rc = encode3_cached(&map_blo2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_lo, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, rows2, CU_TENSOR_MAP_SWIZZLE_128B, who);
+    }
+    if (rc) return rc;
     nc_prep_kernel<MODE><<<dim3((tx + PT - 1) / PT, b), 256, prep_smem, stream>>>(b_src0, b_src1, b_hi, b_lo, colv, isb, c, tx, pl.K, pl.Kpad, pl.NT, temperature);
     ++alb::g_launches;
-    CUtensorMap map_a, map_bhi, map_blo, map_bhi2, map_blo2;
-    int rc = encode3(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_src, (uint64_t)ty, (uint64_t)c, (uint64_t)b, BM, RAW_CH, CU_TENSOR_MAP_SWIZZLE_NONE, who);
-    if (!rc) rc = encode3(&map_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_hi, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, (uint32_t)pl.NB, CU_TENSOR_MAP_SWIZZLE_128B, who);
-    if (!rc) rc = encode3(&map_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_lo, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, (uint32_t)pl.NB, CU_TENSOR_MAP_SWIZZLE_128B, who);
-    const uint32_t rows2 = pl.npass > 1 ? (uint32_t)(pl.NT - 256) : (uint32_t)pl.NB;        // second token block of a long text
-    if (!rc) rc = encode3(&map_bhi2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_hi, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, rows2, CU_TENSOR_MAP_SWIZZLE_128B, who);
-    if (!rc) rc = encode3(&map_blo2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_lo, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, rows2, CU_TENSOR_MAP_SWIZZLE_128B, who);
-    if (rc) return rc;
     V2Params p;
     memset(&p, 0, sizeof(p));
     p.a_src = a_src; p.b_src0 = b_src0; p.b_src1 = b_src1; p.colv = colv; p.inv_sb = isb; p.prior = prior; p.x_lengths = x_lengths; p.out = out;
