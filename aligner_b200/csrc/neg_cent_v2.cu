@@ -422,19 +422,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
     if (wid == 0) {
         // ================= TMA producer, mel side: raw z / q boxes (HBM latency: runs as far ahead as the ring allows) =================
         if (lane == 0) {
-            uint32_t rc = 0;
+            uint32_t rc = 0, rs = 0, rph = 0;                 // ring cursor (no divisions by the runtime stage count)
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int b, mt;
                 item_to_tile(p, item, b, mt);
                 const int y0 = mt * BM;
                 // (a text longer than 256 tokens is two token blocks of the SAME mel-side operand: it is loaded and converted once)
                     for (int ch = 0; ch < p.nchunks * RPC; ++ch, ++rc) {
-                        const uint32_t rs = rc % SR, rph = (rc / SR) & 1u;
                         NC_STAMP(0, rc, 0);
                         mbar_wait(bar_raw_empty + 8 * rs, rph ^ 1u);
                         NC_STAMP(0, rc, 1);
                         mbar_expect_tx(bar_raw_full + 8 * rs, RAW_BYTES);
                         tma_load_3d(raw0 + rs * RAW_BYTES, &map_a, y0, ch * RAW_CH, b, bar_raw_full + 8 * rs);
+                        if (++rs == (uint32_t)SR) { rs = 0; rph ^= 1u; }
                     }
             }
         }
@@ -444,12 +444,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
             // programmatic dependent launch: this kernel may have started while nc_prep_kernel was still running (its prologue and
             // the mel-side loads / conversion do not depend on it); the text-side operand must be complete before it is read
             asm volatile("griddepcontrol.wait;" ::: "memory");
-            uint32_t cc = 0;
+            uint32_t cc = 0, s = 0, ph = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int b, mt;
                 item_to_tile(p, item, b, mt);
                     for (int ch = 0; ch < p.nchunks; ++ch, ++cc) {
-                        const uint32_t s = cc % SB, ph = (cc / SB) & 1u;
                         NC_STAMP(1, cc, 0);
                         mbar_wait(bar_b_empty + 8 * s, ph ^ 1u);
                         NC_STAMP(1, cc, 1);
@@ -462,6 +461,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                             tma_load_3d(bs + 256u * 128u, &map_bhi2, ch * KC, 256, b, bar_b_full + 8 * s);
                             tma_load_3d(bs + lo + 256u * 128u, &map_blo2, ch * KC, 256, b, bar_b_full + 8 * s);
                         }
+                        if (++s == SB) { s = 0; ph ^= 1u; }
                     }
             }
         }
@@ -469,13 +469,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
             uint32_t cc = 0, it = 0;
+            uint32_t s = 0, ph = 0, sbs = 0, bph = 0;         // A and text-operand ring cursors (no divisions on this thread's critical path)
             bool ready = false;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
                 const uint32_t slot = two_slots ? (it & 1u) : 0u, use = two_slots ? (it >> 1) : it;
                 mbar_wait(bar_t_empty + 8 * slot, (use & 1u) ^ 1u);          // the epilogue has drained this accumulator
                 fence_after();
                 for (int ch = 0; ch < p.nchunks; ++ch, ++cc) {
-                    const uint32_t s = cc % SA, ph = (cc / SA) & 1u, sbs = cc % SB, bph = (cc / SB) & 1u;
                     NC_STAMP(2, cc, 0);
                     if (!ready) {                                                   // (normally already waited for, see below)
                         mbar_wait(bar_a_full + 8 * s, ph);
@@ -510,9 +510,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                         if (pass == p.npass - 1 && ch != p.nchunks - 1 && SB > 1) {
                             // the tensor pipe still has this chunk's first two products queued: the barrier round trips of the
                             // NEXT chunk (same tile) hide behind them instead of opening a gap between the chunks
-                            const uint32_t s2 = (cc + 1) % SA, ph2 = ((cc + 1) / SA) & 1u;
+                            const uint32_t s2 = (s + 1 == (uint32_t)SA) ? 0u : s + 1, ph2 = (s + 1 == (uint32_t)SA) ? ph ^ 1u : ph;
+                            const uint32_t sb2 = (sbs + 1 == SB) ? 0u : sbs + 1, bph2 = (sbs + 1 == SB) ? bph ^ 1u : bph;
                             mbar_wait(bar_a_full + 8 * s2, ph2);
-                            mbar_wait(bar_b_full + 8 * ((cc + 1) % SB), ((cc + 1) / SB) & 1u);
+                            mbar_wait(bar_b_full + 8 * sb2, bph2);
                             ready = true;
                         }
 #endif
@@ -526,6 +527,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                     mma_commit(bar_a_empty + 8 * s);                                // both stages reusable when these MMAs have read them
                     mma_commit(bar_b_empty + 8 * sbs);
                     NC_STAMP(2, cc, 3);
+                    if (++s == (uint32_t)SA) { s = 0; ph ^= 1u; }
+                    if (++sbs == SB) { sbs = 0; bph ^= 1u; }
                 }
                 mma_commit(bar_t_full + 8 * slot);                                  // accumulator complete
             }
@@ -538,13 +541,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
         // The converted chunk lives in registers (hi / lo, eight 16-byte pieces) while its shared-memory stage is still being read by
         // the tensor core: what remains on the critical path after "stage free" is eight stores, a proxy fence and an arrival.
         uint32_t rc = 0, cc = 0, it = 0;
+        uint32_t rs = 0, rph = 0, s = 0, ph = 0;             // ring cursors
         uint32_t H[RPC * (MODE == 0 ? 4 : 2)][4], L[RPC * (MODE == 0 ? 4 : 2)][4];
         const uint32_t total_chunks = (uint32_t)p.nchunks;          // (the mel-side operand of a tile is produced once, whatever the text length)
         bool bad = false;
         auto produce = [&]() {                               // raw boxes of the next chunk -> H / L
 #pragma unroll
             for (int r = 0; r < RPC; ++r, ++rc) {
-                const uint32_t rs = rc % SR, rph = (rc / SR) & 1u;
                 if (t == 0) NC_STAMP(3, cc, 0);
                 mbar_wait(bar_raw_full + 8 * rs, rph);
                 if (t == 0) NC_STAMP(3, cc, 1);
@@ -577,13 +580,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
 #pragma unroll
                         for (int e = 0; e < 4; ++e) split2(kA2 * v[8 * j + 2 * e], kA2 * v[8 * j + 2 * e + 1], H[2 * r + j][e], L[2 * r + j][e]);
                 }
+                if (++rs == (uint32_t)SR) { rs = 0; rph ^= 1u; }
             }
         };
         if (blockIdx.x < p.n_items) produce();
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
             if (t == 0) ovf[(it + 4) & 7] = 0;                // nobody is within four tiles of that slot
             for (uint32_t ci = 0; ci < total_chunks; ++ci, ++cc) {
-                const uint32_t s = cc % SA, ph = (cc / SA) & 1u;
                 const uint32_t sA_hi = a0 + s * 2u * A_TILE + a_row, sA_lo = sA_hi + A_TILE;
                 mbar_wait(bar_a_empty + 8 * s, ph ^ 1u);
                 if (t == 0) NC_STAMP(3, cc, 2);
@@ -611,6 +614,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                 mbar_arrive(bar_a_full + 8 * s);
                 if (kDbg && p.dbg != nullptr && blockIdx.x == 0 && cc < (uint32_t)kDbgSlots)
                     atomicMax(reinterpret_cast<unsigned long long*>(p.dbg) + (3 * kDbgSlots + cc) * 4 + 3, (unsigned long long)clock64());   // LAST arrival
+                if (++s == (uint32_t)SA) { s = 0; ph ^= 1u; }
                 const bool last_of_item = (ci + 1 == total_chunks);
                 if (last_of_item) bad = false;                                // the next chunk belongs to the next tile
                 if (!last_of_item || item + (int)gridDim.x < p.n_items) produce();
