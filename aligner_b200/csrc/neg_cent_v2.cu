@@ -471,6 +471,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
             uint32_t cc = 0, it = 0;
             uint32_t s = 0, ph = 0, sbs = 0, bph = 0;         // A and text-operand ring cursors (no divisions on this thread's critical path)
             bool ready = false;
+            // operand descriptors of every stage, formed once (a k-step is +2 on the 16-byte-unit address field)
+            const uint64_t dA0h = make_desc(a0), dA0l = make_desc(a0 + A_TILE), dA1h = make_desc(a0 + 2u * A_TILE), dA1l = make_desc(a0 + 3u * A_TILE);
+            const uint64_t dB0h = make_desc(b0), dB0l = make_desc(b0 + (uint32_t)p.NT * 128u);
+            const uint64_t dB1h = make_desc(b0 + p.b_stage_bytes), dB1l = make_desc(b0 + p.b_stage_bytes + (uint32_t)p.NT * 128u);
+            const uint32_t idesc0 = make_idesc(min(256, p.NT)), idesc1 = make_idesc(p.NT > 256 ? p.NT - 256 : 16);
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
                 const uint32_t slot = two_slots ? (it & 1u) : 0u, use = two_slots ? (it >> 1) : it;
                 mbar_wait(bar_t_empty + 8 * slot, (use & 1u) ^ 1u);          // the epilogue has drained this accumulator
@@ -485,18 +490,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                     ready = false;
                     NC_STAMP(2, cc, 2);
                     fence_after();
-                    const uint32_t sA_hi = a0 + s * 2u * A_TILE, sA_lo = sA_hi + A_TILE;
                     const int nk = min(4, (K - ch * KC + 15) >> 4);                 // 16-k steps that hold real channels
+                    const uint64_t dAh = s ? dA1h : dA0h, dAl = s ? dA1l : dA0l;
                     // a text longer than 256 tokens: two token blocks = two MMA series into the two TMEM halves, same A stage
                     for (int pass = 0; pass < p.npass; ++pass) {
-                        const int ncols = min(256, p.NT - pass * 256);
-                        const uint32_t idesc = make_idesc(ncols);
+                        const uint32_t idesc = pass ? idesc1 : idesc0;
                         const uint32_t dcol = tmem_base + slot * 256u + (uint32_t)pass * 256u;
-                        const uint32_t sB_hi = b0 + sbs * p.b_stage_bytes + (uint32_t)pass * (256u * 128u), sB_lo = sB_hi + (uint32_t)p.NT * 128u;
-                        // The single issuing thread is on the critical path (12 MMAs of ~110 cycles each per chunk): descriptors are
-                        // formed once per chunk, a k-step is "+2" on the 16-byte-unit address field, and the common case (four
-                        // k-steps) is straight-line code.
-                        const uint64_t dAh = make_desc(sA_hi), dAl = make_desc(sA_lo), dBh = make_desc(sB_hi), dBl = make_desc(sB_lo);
+                        // (second token block: 256 rows = 2048 sixteen-byte units further into the stage)
+                        const uint64_t dBh = (sbs ? dB1h : dB0h) + (pass ? 2048u : 0u), dBl = (sbs ? dB1l : dB0l) + (pass ? 2048u : 0u);
                         if (nk == 4) {
                             mma_f16(dcol, dAh, dBh, idesc, ch ? 1u : 0u);                                  // hi * hi
                             mma_f16_acc(dcol, dAh + 2, dBh + 2, idesc); mma_f16_acc(dcol, dAh + 4, dBh + 4, idesc); mma_f16_acc(dcol, dAh + 6, dBh + 6, idesc);
