@@ -155,60 +155,64 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
 // Each row is scaled by a power of two to [2^14, 2^15), split into fp16 hi / lo and written K-contiguous ([b, Tx, Kpad], what the
 // SWIZZLE_128B tensor map of the main kernel reads); k >= K is zero.
 constexpr int PT = 8;                         // tokens per prep CTA
-constexpr int PCH = 8;                        // channels a prep thread loads per batch (all in flight together)
+constexpr int PG = 16;                        // channel groups per prep CTA (PT * PG = 128 threads: 16 CTAs per SM, one wave for 64 x 200 tokens)
+constexpr int PCH = 12;                       // channels a prep thread loads per batch (all in flight together: one DRAM round trip up to C = 192)
 template <int MODE>
-__global__ void __launch_bounds__(256) nc_prep_kernel(const float* __restrict__ src0, const float* __restrict__ src1, __half* __restrict__ b_hi,
-                                                      __half* __restrict__ b_lo, float* __restrict__ colv, float* __restrict__ inv_sb, int C, int Tx,
-                                                      int K, int Kpad, int TxS, float temperature)
+__global__ void __launch_bounds__(PT * PG) nc_prep_kernel(const float* __restrict__ src0, const float* __restrict__ src1, __half* __restrict__ b_hi,
+                                                          __half* __restrict__ b_lo, float* __restrict__ colv, float* __restrict__ inv_sb, int C, int Tx,
+                                                          int K, int Kpad, int TxS, float temperature)
 {
     extern __shared__ __align__(16) float vals[];              // [PT][Kpad + 4]
-    __shared__ float part_max[32][PT], part_sum[32][PT], row_scale[PT];
+    __shared__ float part_max[PG / 4][PT], part_sum[PG / 4][PT], row_scale[PT];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the score kernel may start its prologue and its mel-side work now
-    const int tid = threadIdx.x, tok = tid & (PT - 1), grp = tid >> 3;      // 32 channel groups
+    const int tid = threadIdx.x, tok = tid & (PT - 1), grp = tid >> 3;      // PG channel groups; a warp holds 4 of them for all 8 tokens
     const int b = blockIdx.y, x = blockIdx.x * PT + tok;
     const int VS = Kpad + 4;
     const bool ok = x < Tx;
-    const size_t cstep = (size_t)32 * Tx;                        // this thread's channels are grp, grp + 32, ...
+    const size_t cstep = (size_t)PG * Tx;                        // this thread's channels are grp, grp + PG, ...
     const float* p0 = src0 + (size_t)b * C * Tx + (size_t)grp * Tx + (ok ? x : 0);
     const float* p1 = MODE == 0 ? src1 + (size_t)b * C * Tx + (size_t)grp * Tx + (ok ? x : 0) : nullptr;
     float* vrow = vals + tok * VS + (MODE == 0 ? 2 * grp : grp);
     float mx = 0.f, sum = 0.f;
-    for (int c0 = grp; c0 < C; c0 += 32 * PCH) {
+    for (int c0 = grp; c0 < C; c0 += PG * PCH) {
         float a[PCH], l[PCH];
 #pragma unroll
         for (int u = 0; u < PCH; ++u) {                          // all loads of the batch first: one DRAM round trip
-            const bool in = ok && (c0 + 32 * u < C);
+            const bool in = ok && (c0 + PG * u < C);
             a[u] = in ? p0[u * cstep] : 0.f;
             if (MODE == 0) l[u] = in ? p1[u * cstep] : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < PCH; ++u) {
-            if (c0 + 32 * u < C) {
+            if (c0 + PG * u < C) {
                 if (MODE == 0) {
                     const float mm = a[u], lg = l[u];
                     const float s2 = fast_exp(-2.f * lg), ms2 = mm * s2;
                     if (ok) sum += (-0.9189385332046727f - lg) - 0.5f * mm * ms2;      // -0.5 log(2 pi) - logs - 0.5 m^2 s2
                     const float v0 = ok ? s2 * kB1 : 0.f, v1 = ok ? ms2 * kB2 : 0.f;
-                    *reinterpret_cast<float2*>(vrow + 64 * u) = make_float2(v0, v1);
+                    *reinterpret_cast<float2*>(vrow + 2 * PG * u) = make_float2(v0, v1);
                     mx = fmaxf(mx, fmaxf(fabsf(v0), fabsf(v1)));
                 } else {
                     sum = fmaf(a[u], a[u], sum);
                     const float v0 = a[u] * kB2;
-                    vrow[32 * u] = v0;
+                    vrow[PG * u] = v0;
                     mx = fmaxf(mx, fabsf(v0));
                 }
             }
         }
-        p0 += PCH * cstep; vrow += (MODE == 0 ? 64 : 32) * PCH;
+        p0 += PCH * cstep; vrow += (MODE == 0 ? 2 * PG : PG) * PCH;
         if (MODE == 0) p1 += PCH * cstep;
     }
-    for (int k = K + grp; k < Kpad; k += 32) vals[tok * VS + k] = 0.f;
-    part_max[grp][tok] = mx; part_sum[grp][tok] = sum;
+    for (int k = K + grp; k < Kpad; k += PG) vals[tok * VS + k] = 0.f;
+    // per-token maximum and sum: the four channel groups of a warp by shuffles (lanes 8 apart hold the same token), fixed order
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8)); sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16)); sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+    if ((tid & 31) < PT) { part_max[tid >> 5][tok] = mx; part_sum[tid >> 5][tok] = sum; }
     __syncthreads();
     if (tid < PT) {
         float m8 = part_max[0][tid], s8 = part_sum[0][tid];
 #pragma unroll
-        for (int g = 1; g < 32; ++g) { m8 = fmaxf(m8, part_max[g][tid]); s8 += part_sum[g][tid]; }      // fixed order: deterministic
+        for (int g = 1; g < PG / 4; ++g) { m8 = fmaxf(m8, part_max[g][tid]); s8 += part_sum[g][tid]; }      // fixed order: deterministic
         // power-of-two scale that puts the row maximum into [2^14, 2^15); rows of zeros (or non-finite rows) keep scale 1
         float sc = 1.f;
         if (m8 > 0.f && m8 < 3.0e38f) {
@@ -230,10 +234,11 @@ __global__ void __launch_bounds__(256) nc_prep_kernel(const float* __restrict__ 
         }
     }
     __syncthreads();
-    // one warp per token row, lanes over its 16-byte chunks (8 fp16): coalesced 512-byte stores, no index arithmetic
+    // one warp per pair of token rows, lanes over a row's 16-byte chunks (8 fp16): coalesced 512-byte stores
     const int cpr = Kpad >> 3;
-    const int r = tid >> 5, xr = blockIdx.x * PT + r;
-    if (xr < Tx) {
+    for (int r = tid >> 5; r < PT; r += PT * PG / 32) {
+        const int xr = blockIdx.x * PT + r;
+        if (xr >= Tx) continue;
         const float sc = row_scale[r];
         const float* vr = vals + r * VS;
         __half* oh = b_hi + ((size_t)b * Tx + xr) * Kpad;
@@ -981,7 +986,7 @@ static int run(const float* a_src, const float* b_src0, const float* b_src1, con
         if (!rc) rc = encode3_cached(&map_blo2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_lo, (uint64_t)pl.Kpad, (uint64_t)tx, (uint64_t)b, KC, rows2, CU_TENSOR_MAP_SWIZZLE_128B, who);
     }
     if (rc) return rc;
-    nc_prep_kernel<MODE><<<dim3((tx + PT - 1) / PT, b), 256, prep_smem, stream>>>(b_src0, b_src1, b_hi, b_lo, colv, isb, c, tx, pl.K, pl.Kpad, pl.NT, temperature);
+    nc_prep_kernel<MODE><<<dim3((tx + PT - 1) / PT, b), PT * PG, prep_smem, stream>>>(b_src0, b_src1, b_hi, b_lo, colv, isb, c, tx, pl.K, pl.Kpad, pl.NT, temperature);
     ++alb::g_launches;
     V2Params p;
     memset(&p, 0, sizeof(p));
