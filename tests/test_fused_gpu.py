@@ -76,6 +76,35 @@ def test_fused_with_the_reference_style_mask(mods):
     assert (path.cpu().numpy().astype(np.int32) == ref).mean() >= 0.9999
 
 
+def test_fused_shape_fuzz(mods):
+    """Random shapes and ragged lengths (empty items included) through the fused entry, pipelined whenever possible."""
+    fused, ma, nc, _lib = mods
+    rng = np.random.default_rng(4242)
+    g = torch.Generator(device="cuda").manual_seed(4242)
+    _lib.set_option("fused_seq", "2")
+    try:
+        for trial in range(30):
+            b = int(rng.integers(1, 40))
+            c = int(rng.choice([8, 33, 80, 192]))
+            tx = int(rng.choice([1, 7, 31, 64, 130, 257, 300, 500]))
+            ty = 4 * int(rng.integers(max(1, (tx + 3) // 4), max(2, (tx + 3) // 4) + 200))
+            z = torch.randn(b, c, ty, generator=g, device="cuda")
+            m = torch.randn(b, c, tx, generator=g, device="cuda")
+            logs = torch.rand(b, c, tx, generator=g, device="cuda") * 1.5 - 1.0
+            t_x = rng.integers(1, tx + 1, b).astype(np.int32)
+            t_y = np.array([rng.integers(t_x[i], ty + 1) for i in range(b)], np.int32)
+            if b > 2:
+                t_x[1] = 0                                     # an empty item
+            xl, yl = torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda()
+            score = nc.gaussian_neg_cent(z, m, logs)
+            want = ma.maximum_path_lengths(score, xl, yl, return_durations=True)
+            path, neg_cent, dur = fused.gaussian_maximum_path(z, m, logs, x_lengths=xl, y_lengths=yl, return_durations=True)
+            assert torch.equal(neg_cent, score), (b, c, tx, ty)
+            assert torch.equal(path, want["path"]) and torch.equal(dur, want["durations"]), (b, c, tx, ty)
+    finally:
+        _lib.set_option("fused_seq", None)
+
+
 def test_fused_soak(mods):
     """Many back-to-back fused calls on alternating shapes: the publish / wait hand-off between the two concurrent kernels."""
     fused, ma, nc, _lib = mods

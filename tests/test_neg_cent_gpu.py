@@ -172,6 +172,32 @@ def test_ota_with_generated_beta_binomial_prior(nc, b, c, tx, ty, scaling, nativ
     assert np.abs(mine - dense).max() <= 1e-6
 
 
+def test_shape_fuzz_tma_path(nc):
+    """Random small shapes through the TMA / tcgen05 kernels (t_mel % 4 == 0, t_x <= 512): channel tails, token tails around the
+    16 / 256 boundaries, mel tiles shorter than 128 frames, one utterance to several rounds of tiles, ragged x_lengths."""
+    from aligner_b200 import _lib
+    rng = np.random.default_rng(777)
+    g = torch.Generator(device="cuda").manual_seed(777)
+    txs = [1, 2, 15, 16, 17, 31, 100, 255, 256, 257, 272, 300, 511, 512]
+    for trial in range(40):
+        b = int(rng.integers(1, 5))
+        c = int(rng.choice([1, 3, 15, 16, 17, 31, 32, 33, 64, 80, 100, 192]))
+        tx = int(rng.choice(txs))
+        ty = 4 * int(rng.integers(1, 100))
+        z = torch.randn(b, c, ty, generator=g, device="cuda")
+        m = torch.randn(b, c, tx, generator=g, device="cuda")
+        logs = torch.rand(b, c, tx, generator=g, device="cuda") * 1.5 - 1.0
+        n0 = _lib.launch_count()
+        got = nc.gaussian_neg_cent(z, m, logs)
+        assert _lib.launch_count() - n0 == 2, (b, c, tx, ty)          # prep + TMA kernel
+        want = nc_oracle.gaussian_neg_cent(z.cpu().numpy(), m.cpu().numpy(), logs.cpu().numpy())
+        assert rel_err(got.cpu().numpy(), want) <= TOL, ("gaussian", b, c, tx, ty)
+        xl = torch.from_numpy(rng.integers(1, tx + 1, b).astype(np.int32)).cuda()
+        got = nc.ota_log_prob(z, m, 0.0005, None, xl)
+        want = nc_oracle.ota_log_prob(z.cpu().numpy(), m.cpu().numpy(), 0.0005, None, xl.cpu().numpy())
+        assert rel_err(got.cpu().numpy(), want) <= TOL, ("ota", b, c, tx, ty)
+
+
 def test_c_entry_without_workspace(nc):
     """alb200_neg_cent_gaussian / _ota (no scratch argument) take the scratch from the stream-ordered allocator."""
     from aligner_b200 import _lib
