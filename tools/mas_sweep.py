@@ -72,7 +72,7 @@ def main():
         "c1": (16, 100, 800, False, [None, "2,32,4,1,0", "2,32,4,1,1", "1,32,4,1,1", "1,32,8,1,1", "1,32,4,1,0", "3,32,4,1,1", "4,32,4,1,1"]),
         "c2": (64, 200, 1000, False, [None, "2,32,4,1,0", "2,32,4,1,1", "2,32,5,1,1", "1,32,4,1,1", "1,32,3,1,1", "1,32,4,0,1,2", "1,32,3,0,1,2",
                                       "2,32,4,0,1,2"]),
-        "c3": (32, 300, 1500, False, [None, "3,32,3,0,0", "3,32,3,0,1", "3,32,4,0,1", "4,32,3,0,1", "2,32,3,0,1", "2,32,4,0,1", "1,32,3,0,1"]),
+        "c3": (32, 300, 1500, False, [None, "3,32,3,0,1", "2,32,4,0,1,2", "2,32,3,0,1,2", "2,32,6,0,1,2", "3,32,3,0,1,2"]),
         "c4": (8, 1000, 6000, False, [None, "8,16,2,0,0,1", "2,32,3,0,1,4", "2,32,2,0,1,4", "3,32,2,0,1,3", "4,32,2,0,1,2", "4,32,3,0,1,2", "1,32,4,0,1,8"]),
         "c4b": (16, 768, 3072, False, [None, "6,16,4,0,0,1", "2,32,3,0,1,3", "3,32,2,0,1,2", "4,32,2,0,1,2"]),
         "c4c": (32, 640, 3200, False, [None, "6,16,4,0,0,1", "2,32,3,0,1,3", "4,32,2,0,1,2"]),
