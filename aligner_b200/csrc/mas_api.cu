@@ -102,10 +102,13 @@ struct KEntry { int R, TF, skew, nwmax, minb; KernelFn fn; int vt; };     // vt:
 #define ALB_K8(R, TF) { R, TF, 0, 8, 1, mas_kernel<R, TF, false, 8, 1> }
 #define ALB_KC(R) { R, 32, 2, 4, 1, mas_kernel<R, 32, true, 4, 1, true> }      // skew code 2 = skewed + cluster hand-off
 #define ALB_KS8(R) { R, 32, 1, 8, 1, mas_kernel<R, 32, true, 8, 1> }
+#define ALB_KL4(R) { R, 32, 4, 4, 1, mas_kernel<R, 32, true, 4, 1, false, 0, false, kLag4> }   // skew code 4 = skewed, 4-frame lag, pre-skewed boxes
 static const KEntry g_kernels[] = {
 #ifdef ALB200_FEW_KERNELS          // A/B builds while tuning (build_lib.py --variant): the instances of the latency regime + one throughput instance
     ALB_K(2, 32), ALB_K(4, 16), ALB_KS(1), ALB_KS(2), ALB_KS(3), ALB_KS8(1), ALB_KC(1), ALB_KC(2),
+    ALB_KL4(2), ALB_KL4(3), ALB_KL4(4),
 #else
+    ALB_KL4(2), ALB_KL4(3), ALB_KL4(4),
     ALB_K(1, 32),
     ALB_K(2, 32), ALB_K(2, 16),
     ALB_K(3, 32), ALB_K(3, 16),
@@ -158,11 +161,24 @@ static KernelFn find_kernel(int R, int TF, int skew, int nw, int minb, int vt)
 }
 
 struct Config {
-    int R, TF, NW, NS, bits_smem, skew, grid, occ, nc;
+    int R, TF, NW, NS, bits_smem, skew, grid, occ, nc, lag;
     uint32_t smem;
     int64_t bits_slot_words;
     KernelFn fn;
 };
+
+// 4-frame-lag form (forward_unit4): measured per 32-frame unit of a compute warp (tools/lag_sweep.py, slope between t_y = 1000
+// and 2000, cycles): 1-frame lag R=1/2/3 1140/1120/1350; 4-frame lag R=2/3/4/5/6/8 1060/1210/1390/1690/1850/2360 -- 5-10 % less per
+// unit at equal R, but 124 instead of 31 frames of fill per warp (three more units) and 128 more per hand-off.  That only pays for
+// ONE compute warp and a long mel axis (64x96x2000: 60.3 -> 58.0 us, 64x64x2000: 53.8 -> 52.6 us; 64x200x1000 loses 10 %).
+static bool choose_lag4(int tx, int ty, int* r4, int* nw4)
+{
+    if (tx > 96 || ty < 1536) return false;
+    const int R = (tx + 31) / 32;
+    if (R < 2 || tx % R != 0) return false;
+    *r4 = R; *nw4 = 1;
+    return true;
+}
 
 // Picks rows-per-lane, tile width, ring depth and where the direction bits live.
 //   latency regime   (b <= #SM): one CTA per SM, <= 4 compute warps when possible (one per scheduler), 255-register
@@ -189,10 +205,10 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
         R = tx <= 64 ? 2 : (tx <= 512 ? 4 : (tx <= 2048 ? 8 : 16));
         NW = (tx + 32 * R - 1) / (32 * R);
     }
-    int f_tf = 0, f_ns = 0, f_bits = -1, f_skew = -1, f_nc = 0;
+    int f_tf = 0, f_ns = 0, f_bits = -1, f_skew = -1, f_nc = 0, f_lag = 0;
     int fr = 0;
-    if (opts().force[0])                           // "R,TF,NS,bits_smem,skew,cluster" -- tuning / tests only
-        sscanf(opts().force, "%d,%d,%d,%d,%d,%d", &fr, &f_tf, &f_ns, &f_bits, &f_skew, &f_nc);
+    if (opts().force[0])                           // "R,TF,NS,bits_smem,skew,cluster,lag" -- tuning / tests only
+        sscanf(opts().force, "%d,%d,%d,%d,%d,%d,%d", &fr, &f_tf, &f_ns, &f_bits, &f_skew, &f_nc, &f_lag);
     // Cluster mode: an utterance whose text axis needs more than 4 rows per lane in one CTA (t_x > 512) loses the fast
     // skewed form; split its rows over the CTAs of a thread-block cluster instead (2 rows per lane, 4 compute warps per
     // CTA, boundary rows handed over through distributed shared memory).  Only when every cluster gets its own SMs.
@@ -204,6 +220,18 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     }
     if (NC > 1 && fr == 0) { R = 2; NW = 4; }
     if (fr > 0) { R = fr; NW = (tx + 32 * R * NC - 1) / (32 * R * NC); }
+    // 4-frame lag on pre-skewed boxes (forward_unit4): fewer instructions per frame, but 124 frames of fill per warp instead of 31.
+    // fp32 [t_text, t_mel] scores, one CTA per utterance, t_x a multiple of the rows per lane (a lane's rows must not run past
+    // the tensor).  Chosen where measured faster (choose_lag4); any other shape only through the force option.
+    int lag = 1;
+    const bool lag4_ok = latency && aligned && vt == 0 && !vl && NC == 1 && tx > 32 && f_skew != 0;
+    if (f_lag == kLag4) {
+        if (!lag4_ok || fr == 0 || tx % R != 0 || NW > 4) return fail(ALB200_E_UNSUPPORTED, "the 4-frame-lag form cannot take t_x=%s%lld at %lld rows per lane", "", tx, R);
+        lag = kLag4;
+    } else if (lag4_ok && fr == 0 && f_lag == 0 && b <= di.sms) {
+        int r4 = 0, nw4 = 0;
+        if (choose_lag4(tx, ty, &r4, &nw4)) { lag = kLag4; R = r4; NW = nw4; }
+    }
     if (NC > 1 && (!aligned || NC > 8 || 32 * R * NW * NC < tx))
         return fail(ALB200_E_UNSUPPORTED, "cluster of %s%lld CTAs cannot take t_x=%lld", "", NC, tx);
     if (NW > kMaxWarps)
@@ -216,7 +244,7 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     // dependency chain; costs 31 frames of fill per warp and 32 more per warp hand-off.  32-frame tiles only.  Measured
     // (profiles/r01_skew_sweep.json): faster or equal wherever an utterance owns its SM and has <= 4 rows per lane.
     int want_skew = f_skew >= 0 ? f_skew : ((latency && R <= 4) ? 1 : 0);
-    if (NC > 1) want_skew = 1;
+    if (NC > 1 || lag == kLag4) want_skew = 1;
     if (vl && (NC > 1 || vt != 0)) return fail(ALB200_E_UNSUPPORTED, "the [t_mel, t_text] layout has fp32 single-CTA kernels only%s", "");
     if (!aligned || R > 8) want_skew = 0;                      // its tiles come in by TMA: 16-byte aligned rows, <= 256 rows per box
     auto try_fit = [&](int tf, int ns, int bs, int budget) -> bool {
@@ -226,7 +254,7 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
         if (f_ns && ns != f_ns) return false;
         if (f_bits >= 0 && bs != f_bits) return false;
         if (NC > 1 && bs != 0) return false;                   // the walker (CTA 0) reads every CTA's bits: L2 slot
-        const SmemLayout L = make_layout(NW, ns, R, tf, bs, nblk, want_dur, want_skew, NC, vt ? 2 : 4);
+        const SmemLayout L = make_layout(NW, ns, R, tf, bs, nblk, want_dur, want_skew, NC, vt ? 2 : 4, lag);
         if ((int64_t)L.total > budget) return false;
         best_tf = tf; best_ns = ns; best_bits = bs;
         return true;
@@ -234,7 +262,7 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
     if (latency) {
         // deepest ring that fits one CTA per SM, bits in shared memory when possible
         for (int pass = 0; pass < 4 && !best_tf; ++pass) {
-            if (pass == 2) { if (f_skew >= 0 || !want_skew) break; want_skew = 0; }    // does not fit skewed: lock-step
+            if (pass == 2) { if (f_skew >= 0 || !want_skew || lag == kLag4) break; want_skew = 0; }    // does not fit skewed: lock-step
             const int p2 = pass & 1;
             for (int ti = 0; ti < 3 && !best_tf; ++ti)
                 for (int bs = 1; bs >= 0 && !best_tf; --bs)
@@ -253,14 +281,15 @@ static int select_config_uncached(const DevInfo& di, int b, int tx, int ty, bool
         return fail(ALB200_E_UNSUPPORTED, "t_x=%s%lld does not fit the shared-memory ring (max about 3300)", "", tx);
     c->R = R; c->TF = best_tf; c->NW = NW; c->NS = best_ns; c->bits_smem = best_bits; c->nc = NC;
     c->skew = want_skew;
+    c->lag = lag;
     c->fn = nullptr;
     if (!latency && !c->skew)
         for (const KEntry& k : g_kernels)
             if (k.R == R && k.TF == best_tf && k.skew == 0 && NW <= k.nwmax && k.minb == 2 && k.vt == vt) { c->fn = k.fn; break; }
     if (vl && !c->skew) return fail(ALB200_E_UNSUPPORTED, "the [t_mel, t_text] layout needs the skewed/TMA form (latency regime, <= 4 rows per lane, 16-byte aligned rows)%s", "");
-    if (!c->fn) c->fn = find_kernel(R, best_tf, vl ? 3 : (NC > 1 ? 2 : c->skew), NW, latency ? 1 : 2, vt);
+    if (!c->fn) c->fn = find_kernel(R, best_tf, vl ? 3 : (NC > 1 ? 2 : (lag == kLag4 ? 4 : c->skew)), NW, latency ? 1 : 2, vt);
     if (!c->fn) return fail(ALB200_E_UNSUPPORTED, "no kernel instance for R=%s%lld TF=%lld (score type %lld)", "", R, best_tf, vt);
-    SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur, want_skew, NC, vt ? 2 : 4);
+    SmemLayout L = make_layout(NW, best_ns, R, best_tf, best_bits, nblk, want_dur, want_skew, NC, vt ? 2 : 4, lag);
     c->smem = L.total;
     c->bits_slot_words = (int64_t)nblk * NC * NW * 32 * R;
     ALB_CUDA(cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));   // once per instance, never lowered
@@ -356,6 +385,36 @@ static int values_tensor_map(const void* values, int vt, int vl, int b, int tx, 
     return 0;
 }
 
+// Pre-skewed boxes for the 4-frame-lag form: values viewed as (frame, lane, row) with lane stride R*t_y*4 - 16 bytes -- one lane
+// further is R rows down and four frames back.  Box = (32 frames, 32 lanes, R rows), 128-byte swizzle; `lanes` bounds the lane
+// coordinate (lanes past it are zero-filled without a fetch) and t_y + 4*(lanes-1) bounds the frame coordinate, so the last lane
+// never reads past its row's end (tools/micro/tma_lag4_test.cu checks both under compute-sanitizer).
+static int values_tensor_map_lag4(const void* values, int b, int tx, int ty, int R, int lanes, CUtensorMap* out)
+{
+    TmapEncodeFn enc = tmap_encode_fn();
+    if (!enc) return fail(ALB200_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver%s", "");
+    struct Key { const void* v; int b, tx, ty, R, lanes; unsigned gen; };
+    static thread_local Key keys[16];
+    static thread_local CUtensorMap maps[16];
+    static thread_local int used = 0, next = 0;
+    for (int i = 0; i < used; ++i)
+        if (keys[i].v == values && keys[i].gen == opts().gen && keys[i].b == b && keys[i].tx == tx && keys[i].ty == ty && keys[i].R == R && keys[i].lanes == lanes) {
+            *out = maps[i];
+            return 0;
+        }
+    if ((int64_t)b * tx > 0x7fffffffLL) return fail(ALB200_E_UNSUPPORTED, "b * t_x = %s%lld rows exceed the tensor-map coordinate range", "", (long long)b * tx);
+    if (lanes < 1 || lanes > 32) return fail(ALB200_E_INVALID, "bad lane count %s%lld for the pre-skewed tensor map", "", lanes);
+    cuuint64_t dims[3] = { (cuuint64_t)ty + (cuuint64_t)kLag4 * (lanes - 1), (cuuint64_t)lanes, (cuuint64_t)b * (cuuint64_t)tx };
+    cuuint64_t strides[2] = { (cuuint64_t)R * ty * 4 - 16, (cuuint64_t)ty * 4 };
+    cuuint32_t box[3] = { 32, 32, (cuuint32_t)R }, es[3] = { 1, 1, 1 };
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(values), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ALB200_E_CUDA, "cuTensorMapEncodeTiled (pre-skewed box) failed with %s%lld", "", (long long)r);
+    keys[next] = Key{ values, b, tx, ty, R, lanes, opts().gen }; maps[next] = *out;
+    next = (next + 1) % 16; if (used < 16) ++used;
+    return 0;
+}
+
 static size_t ws_bytes_for(const Config& c)
 {
     return sizeof(WsHeader) + (c.bits_smem ? 0 : (size_t)(c.grid / c.nc) * c.bits_slot_words * 4);
@@ -396,7 +455,7 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
     p.B = b; p.Tx = tx; p.Ty = ty; p.esize = esize; p.zero_fill = zero_fill;
     p.nw = c.NW; p.ns = c.NS; p.nblk = (ty + 31) / 32; p.nc = c.nc;
     {
-        const SmemLayout L = make_layout(c.NW, c.NS, c.R, c.TF, c.bits_smem, p.nblk, durations != nullptr, c.skew, c.nc, vt ? 2 : 4);
+        const SmemLayout L = make_layout(c.NW, c.NS, c.R, c.TF, c.bits_smem, p.nblk, durations != nullptr, c.skew, c.nc, vt ? 2 : 4, c.lag);
         p.off_full = L.off_full; p.off_empty = L.off_empty; p.off_xbar = L.off_xbar; p.off_flags = L.off_flags; p.off_misc = L.off_misc; p.off_bnd = L.off_bnd;
         p.off_zero = L.off_zero; p.off_ring = L.off_ring; p.off_bits = L.off_bits; p.off_dur = L.off_dur; p.off_bt = L.off_bt; p.stage_bytes = L.stage_bytes;
     }
@@ -406,7 +465,14 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
     CUtensorMap tmap_tail;
     memset(&tmap_tail, 0, sizeof(tmap_tail));
     p.tail_rows = 32 * c.R;
-    if (c.skew) {
+    if (c.lag == kLag4) {
+        // full warps: 32 lanes, frames may run 124 past a row's end (into the next row, which exists: they are not the last warp);
+        // last warp: only the lanes that have rows, and a frame extent that keeps its last lane inside the last row
+        const int last_rows = tx - (c.NW - 1) * 32 * c.R;
+        rc = values_tensor_map_lag4(values, b, tx, ty, c.R, 32, &tmap);
+        if (!rc) rc = values_tensor_map_lag4(values, b, tx, ty, c.R, last_rows / c.R, &tmap_tail);
+        if (rc) return rc;
+    } else if (c.skew) {
         rc = values_tensor_map(values, vt, vl, b, tx, ty, 32 * c.R, c.TF, &tmap);
         if (rc) return rc;
         // rows the last compute warp of the padded text axis really has, rounded up to 8 (TMA box rows are not free)
@@ -604,7 +670,7 @@ int alb200_mas_describe(int b, int tx, int ty, int want_durations, char* buf, si
     if (rc) return rc;
     if (buf && buf_bytes)
         snprintf(buf, buf_bytes, "rows_per_lane=%d tile_frames=%d warps=%d stages=%d bits=%s form=%s smem=%u grid=%d ctas_per_sm=%d cluster=%d",
-                 c.R, c.TF, c.NW, c.NS, c.bits_smem ? "smem" : "global", c.skew ? "skewed" : "lockstep", c.smem, c.grid, c.occ, c.nc);
+                 c.R, c.TF, c.NW, c.NS, c.bits_smem ? "smem" : "global", c.lag == kLag4 ? "skewed4" : (c.skew ? "skewed" : "lockstep"), c.smem, c.grid, c.occ, c.nc);
     return 0;
 }
 

@@ -53,6 +53,8 @@ namespace alb {
 
 constexpr int kMaxWarps = 8;       // compute warps per CTA (an equal number of loader warps rides along)
 constexpr int kRing = 128;         // frames in a warp-boundary ring
+constexpr int kRing4 = 256;        // ... of the 4-frame-lag form (its consumer trails the producer by >= 160 steps)
+constexpr int kLag4 = 4;           // frames lane l trails lane l-1 in the pre-skewed form (the granularity TMA can shift a row by: 16 bytes)
 constexpr int kZeroChunk = 7168;   // bytes per zero-fill bulk store (56 x 128; sized so 2 CTAs x 3 stages still fit an SM at t_x = 400)
 constexpr int kLanePad = 16;       // bytes of skew per lane inside a tile stage
 constexpr int kSkewLag = 1;        // frames lane l trails lane l-1 in the skewed form
@@ -62,6 +64,9 @@ constexpr int kProgDone = 0x3fffffff;
 #endif
 #ifndef ALB200_DBG_BUILD
 #define ALB200_DBG_BUILD 0
+#endif
+#ifndef ALB_ABL
+#define ALB_ABL 0        // timing ablations of the skewed unit body (wrong results; build_lib.py --variant): 1 no shuffle, 2 no tile loads, 4 no bits, 8 no boundary ring
 #endif
 constexpr bool kDbgBuild = ALB200_DBG_BUILD != 0;   // per-warp clock64 stamps (developer aid)
 
@@ -116,7 +121,7 @@ __host__ __device__ inline uint32_t alb_align(uint32_t v, uint32_t a) { return (
 
 // dense: the stages are written by 2-D TMA box loads (skewed form): rows back to back, no per-lane skew
 __host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF, int bits_smem, int nblk, int want_dur, int dense = 0, int nc = 1,
-                                                  int elem_bytes = 4)
+                                                  int elem_bytes = 4, int lag = 1)
 {
     SmemLayout L;
     const uint32_t RW = 32u * R;
@@ -125,11 +130,11 @@ __host__ __device__ inline SmemLayout make_layout(int NW, int NS, int R, int TF,
     L.off_full = o;  o += NW * NS * 8;
     L.off_empty = o; o += NW * NS * 8;
     L.off_xbar = o;  o += (nc > 1 ? 4 * 8 : 0);
-    L.off_flags = alb_align(o, 16); o = L.off_flags + (2 * NW + 1) * 4;    // tail (lane 31) and head (lane 0) progress per warp, + the cross-CTA slot
+    L.off_flags = alb_align(o, 16); o = L.off_flags + (2 * NW + 2) * 4;    // tail (lane 31) and head (lane 0) progress per warp, the cross-CTA slot, a scratch word
     L.off_misc = alb_align(o, 16);  o = L.off_misc + 64 + 2 * kMaxWarps * 16; // item/lengths + per-warp partial mask sums
-    L.off_bnd = alb_align(o, 16);   o = L.off_bnd + (NW + 1) * kRing * 4;           // ring 0: constant sentinel (the row above token 0), ring w+1: last row of warp w
+    L.off_bnd = alb_align(o, 16);   o = L.off_bnd + (NW + 1) * (lag == kLag4 ? kRing4 : kRing) * 4;   // ring 0: constant sentinel (the row above token 0), ring w+1: last row of warp w
     L.off_zero = alb_align(o, 128); o = L.off_zero + kZeroChunk;
-    L.off_ring = alb_align(o, 128); o = L.off_ring + NW * NS * L.stage_bytes;
+    L.off_ring = alb_align(o, lag == kLag4 ? 1024 : 128); o = L.off_ring + NW * NS * L.stage_bytes;      // 128-byte-swizzled boxes: 1024-byte atoms
     L.off_bits = alb_align(o, 16);  o = L.off_bits + (bits_smem ? (uint32_t)nblk * NW * RW * 4 : 0);
     L.off_dur = alb_align(o, 16);   o = L.off_dur + (want_dur ? nc * NW * RW * 4 : 0);
     L.off_bt = alb_align(o, 16);    o = L.off_bt + (uint32_t)nblk * 8 + 16;                 // backtrack hand-off: (token, step mask) per 32-frame block + cursor
@@ -189,6 +194,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 // shared -> global bulk store (TMA engine, UBLKCP)
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
@@ -356,6 +365,7 @@ struct Fwd {
     uint32_t wprev[R];   // skewed: the 32 frames before those in wbits (a lane's words straddle two units)
     float up;            // lock-step: neighbour's last row at the previous frame
     float u1, u2;        // skewed: neighbour's last row for the next frame and the one after (shuffles two frames in flight)
+    float u3, u4, u5;    // 4-frame lag: five shuffles in flight
     float bprev;         // lane 0: value of the row above our first row at the frame before this group
     float bprev1;        // skewed, lane 0: ... and at the first frame of this group (the boundary ring is step-indexed)
 };
@@ -370,7 +380,7 @@ struct Fwd {
 template <int R, int TF, int UNIT, bool SKEW, bool DIAG, int VT, bool VL>
 __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint32_t tile_prev, uint32_t bin_addr, uint32_t bout_addr, int Y, int yl,
                                              bool lane0, bool lane31, float neg, int dxy, uint32_t* bits_row, int TXS,
-                                             int y_lo, unsigned span)
+                                             int y_lo, unsigned span, uint32_t* bits_unit)
 {
     constexpr int NG = UNIT / 4;
     static_assert(!SKEW || UNIT == 32, "the skewed form assembles one direction word per 32-frame unit");
@@ -381,7 +391,7 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
     const uint32_t bin_base = bin_addr + (((Y + (SKEW ? 32 : 0)) & (kRing - 1)) << 2);
     const uint32_t bout_base = bout_addr + ((Y & (kRing - 1)) << 2);
 #pragma unroll
-    for (int g = 0; g < NG; ++g) bin[g] = lds128(bin_base + 16 * g);
+    for (int g = 0; g < NG; ++g) bin[g] = (ALB_ABL & 8) ? make_float4(neg, neg, neg, neg) : lds128(bin_base + 16 * g);
     float4 vn[R];
     // Skewed form: the tiles in shared memory are NOT skewed (same 128-bit asynchronous copies as the lock-step form); lane l
     // reads frame Y + k - l, which is tile position k - l of this tile, or 32 + k - l of the previous one while k < l.  One
@@ -442,7 +452,14 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
                 const bool take = move > stay;                      // core.c:19384
                 const float vr = SKEW ? vq[kk & 1][r] : ((k == 0) ? v[r].x : (k == 1) ? v[r].y : (k == 2) ? v[r].z : v[r].w);
                 float res;
-                if (ALB_SPEC_ADD && SKEW) {
+                if (ALB_ABL & 16) {                                 // timing ablation: max + add (not the reference's NaN behaviour)
+                    res = fmaxf(stay, move) + vr;
+                } else if (ALB_ABL & 32) {                          // timing ablation: both sums formed beside the compare, select last
+                    float rs, rm;
+                    asm("add.f32 %0, %2, %4;\n\tadd.f32 %1, %3, %4;" : "=f"(rs), "=f"(rm) : "f"(stay), "f"(move), "f"(vr));
+                    asm("" : "+f"(rs), "+f"(rm));
+                    res = take ? rm : rs;
+                } else if (ALB_SPEC_ADD && SKEW) {
                     // latency regime (one warp per scheduler, chain-bound): both candidate sums are formed while the compare runs and
                     // the select comes last -- the dependent chain per frame is {FADD | FSETP} -> FSEL instead of FSETP -> FSEL -> FADD.
                     // Bit-identical: the selected operand meets the same single fp32 add (core.pyx:30).
@@ -453,25 +470,25 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
                 }
                 if (DIAG) res = (dxy + r > kk) ? neg : res;         // rows above the diagonal stay at the sentinel
                 nv[r] = res;
-                if (take) hb[r] |= (1u << k);
+                if (take && !(ALB_ABL & 4)) hb[r] |= (1u << k);
             }
             if (SKEW) {
                 // lane l-1 is one frame ahead: what it finishes now is what we need the frame after next
                 S.u1 = S.u2;
-                S.u2 = __shfl_up_sync(0xffffffffu, nv[R - 1], 1);
+                S.u2 = (ALB_ABL & 1) ? nv[R - 1] * 0.5f : __shfl_up_sync(0xffffffffu, nv[R - 1], 1);
             } else {
                 S.up = __shfl_up_sync(0xffffffffu, nv[R - 1], 1);
             }
             o4[k] = nv[R - 1];
 #pragma unroll
             for (int r = 0; r < R; ++r) S.old[r] = nv[r];
-            if (SKEW && kk + 2 < UNIT) {
+            if (SKEW && kk + 2 < UNIT && !(ALB_ABL & 2)) {
                 const uint32_t a = (lane <= kk + 2) ? curA : prevA;
 #pragma unroll
                 for (int r = 0; r < R; ++r) vq[kk & 1][r] = ld_val<VT>(a + (kk + 2) * FSTR + r * RSTR);
             }
         }
-        if (lane31) sts128(bout_base + 16 * g, o4[0], o4[1], o4[2], o4[3]);
+        if (lane31 && !(ALB_ABL & 8)) sts128(bout_base + 16 * g, o4[0], o4[1], o4[2], o4[3]);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             S.wbits[r] = __funnelshift_r(S.wbits[r], hb[r], 4);
@@ -483,7 +500,7 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
         // is the 64-bit window shifted right by `lane`
         const int yw = Y - 32;
         if ((unsigned)(yw - y_lo) < span) {
-            uint32_t* brow = bits_row + (int64_t)(yw >> 5) * TXS;
+            uint32_t* brow = bits_unit;                                   // == bits_row + ((Y - 32) >> 5) * TXS, advanced by the caller
 #pragma unroll
             for (int r = 0; r < R; ++r) brow[r] = __funnelshift_r(S.wprev[r], S.wbits[r], lane);
         }
@@ -497,6 +514,85 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
             for (int r = 0; r < R; ++r) brow[r] = wdone[r];
         }
     }
+}
+
+// ------------------------------------------------------------------ forward unit, 4-frame lag on pre-skewed tiles
+// Lane l runs kLag4 = 4 frames behind lane l-1.  Four fp32 frames are 16 bytes -- the granularity by which a tensor map can shift
+// one box row against the next (row stride R*t_y*4 - 16 bytes; box start coordinates themselves must be 16-byte aligned, so a
+// 1-frame skew cannot be had this way: tools/micro/tma_skew_test.cu).  ONE 3-D box load per unit then delivers every lane's own 32
+// frames, 128-byte swizzled: lane l's row r is box row r*32 + l, its frames 4g..4g+3 the 16-byte chunk g ^ (l & 7).  That is one
+// conflict-free LDS.128 per row and four frames, no current/previous-tile select, nothing kept from the previous tile; and the
+// neighbour's value is needed five steps after it was produced, so no shuffle latency is ever exposed.
+// Measured (tools/micro/body2_bench.cu, a lone warp, cycles per frame, R = 2 / 3 / 4): dense tiles with a 1-frame lag 36.6 / 50.2 /
+// 59.6; this form 21.3 / 25.9 / 28.6.  The price is 4*31 frames of fill per warp instead of 31.
+template <int R, bool DIAG>
+__device__ __forceinline__ void forward_unit4(Fwd<R>& S, uint32_t tile_lane, uint32_t xs, uint32_t bin_addr, uint32_t bout_addr, int Y, int yl,
+                                              bool lane0, bool lane31, float neg, int dxy, uint32_t* bits_unit, int y_lo, unsigned span)
+{
+    constexpr int NG = 8;
+    // Boundary ring, indexed by the producer's step: its lane 31 finishes frame f at step f + 124.  Our step Y + kk needs frame
+    // Y + kk - 1 of the row above = slot Y + kk + 123: kk = 0 is the last slot of the previous unit's loads (S.bprev), then
+    // slots Y + 124 .. Y + 154.  The unit's slots may straddle the ring's end: one mask per 16-byte group.
+    float4 bin[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) bin[g] = lds128(bin_addr + (uint32_t)(((Y + 31 * kLag4 + 4 * g) & (kRing4 - 1)) << 2));
+    const uint32_t bout_base = bout_addr + (uint32_t)((Y & (kRing4 - 1)) << 2);     // Y is a multiple of 32: our 32 slots never wrap
+    float4 vg[2][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) vg[0][r] = lds128(tile_lane + r * 4096 + xs);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        if (g + 1 < NG) {
+            const uint32_t a = tile_lane + (((uint32_t)(g + 1) << 4) ^ xs);
+#pragma unroll
+            for (int r = 0; r < R; ++r) vg[(g + 1) & 1][r] = lds128(a + r * 4096);
+        }
+        const float b0 = S.bprev, b1 = bin[g].x, b2 = bin[g].y, b3 = bin[g].z;
+        S.bprev = bin[g].w;
+        uint32_t hb[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) hb[r] = 0u;
+        float o4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int kk = 4 * g + k;
+            const float bk = (k == 0) ? b0 : (k == 1) ? b1 : (k == 2) ? b2 : b3;
+            const float upv = lane0 ? bk : S.u1;
+            float nv[R];
+#pragma unroll
+            for (int r = R - 1; r >= 0; --r) {
+                const float stay = S.old[r];                        // v_cur  (core.pyx:22)
+                const float move = (r == 0) ? upv : S.old[r - 1];   // v_prev (core.pyx:29)
+                const bool take = move > stay;                      // core.c:19384
+                const float4 v4 = vg[g & 1][r];
+                const float vr = (k == 0) ? v4.x : (k == 1) ? v4.y : (k == 2) ? v4.z : v4.w;
+                float res = (take ? move : stay) + vr;              // core.pyx:30
+                if (DIAG) res = (dxy + r > kk) ? neg : res;         // rows above the diagonal stay at the sentinel
+                nv[r] = res;
+                if (take) hb[r] |= (1u << k);
+            }
+            // lane l-1 is four frames ahead: what it finishes now is what we need five steps from now
+            S.u1 = S.u2; S.u2 = S.u3; S.u3 = S.u4; S.u4 = S.u5;
+            S.u5 = __shfl_up_sync(0xffffffffu, nv[R - 1], 1);
+            o4[k] = nv[R - 1];
+#pragma unroll
+            for (int r = 0; r < R; ++r) S.old[r] = nv[r];
+        }
+        if (lane31) sts128(bout_base + 16 * g, o4[0], o4[1], o4[2], o4[3]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) S.wbits[r] = __funnelshift_r(S.wbits[r], hb[r], 4);
+    }
+    // wbits holds our frames [Y - lag, Y - lag + 32), wprev the 32 before: the aligned word this lane completes now is the block
+    // that starts at Y - 32 - (lag & ~31); it is the 64-bit window shifted right by lag & 31
+    const int lagf = Y - yl;
+    const int yw = Y - 32 - (lagf & ~31);
+    if ((unsigned)(yw - y_lo) < span) {
+        uint32_t* brow = bits_unit;                                       // == bits_row + (yw >> 5) * TXS: per-lane base, advanced by the caller
+#pragma unroll
+        for (int r = 0; r < R; ++r) brow[r] = __funnelshift_r(S.wprev[r], S.wbits[r], lagf & 31);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) S.wprev[r] = S.wbits[r];
 }
 
 // ------------------------------------------------------------------ backtrack walker (one warp)
@@ -630,7 +726,7 @@ __device__ __forceinline__ void backtrack_walk(const uint32_t* bits, int TXS, in
 // ------------------------------------------------------------------ the kernel
 // NWMAX bounds the compute warps of an instance (4 -> 256 threads, 8 -> 512 threads).  MINB = 2 holds an instance to 128
 // registers so two CTAs share an SM (throughput regime); MINB = 1 lets an utterance that owns its SM use up to 255.
-template <int R, int TF, bool SKEW, int NWMAX, int MINB, bool CL = false, int VT = 0, bool VL = false>
+template <int R, int TF, bool SKEW, int NWMAX, int MINB, bool CL = false, int VT = 0, bool VL = false, int LAG = 1>
 __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail)
 {
     constexpr int RW = 32 * R;
@@ -639,9 +735,12 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     constexpr int UNIT = (MINB == 1 && TF == 32) ? 32 : (TF < 16 ? TF : 16);
     constexpr int ES = ValT<VT>::bytes;                  // bytes per score
     constexpr int LANE_STRIDE = R * TF * ES + (SKEW ? 0 : kLanePad);   // skewed: dense TMA tiles, the scalar reads of lanes l and frames k - l hit 32 banks
-    constexpr int LAG31 = SKEW ? 31 * kSkewLag : 0;      // frames lane 31 trails lane 0
+    constexpr bool L4 = (LAG == kLag4);                  // 4-frame lag on pre-skewed, swizzled boxes (forward_unit4)
+    static_assert(LAG == 1 || (L4 && SKEW && !CL && VT == 0 && !VL && TF == 32 && MINB == 1), "the 4-frame lag exists for the fp32 skewed/TMA form only");
+    constexpr int LAG31 = SKEW ? 31 * LAG : 0;           // frames lane 31 trails lane 0
+    constexpr int RING = L4 ? kRing4 : kRing;            // slots of a warp-boundary ring
 
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NW = p.nw;
     const int NS = p.ns;
@@ -688,7 +787,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     for (int i = tid; i < kZeroChunk / 16; i += nthr)
         reinterpret_cast<int4*>(smem + L.off_zero)[i] = make_int4(0, 0, 0, 0);
     if (crank == 0)
-        for (int i = tid; i < kRing; i += nthr) reinterpret_cast<float*>(smem + L.off_bnd)[i] = p.neg;
+        for (int i = tid; i < RING; i += nthr) reinterpret_cast<float*>(smem + L.off_bnd)[i] = p.neg;
     fence_mbar_init();
     fence_proxy_async_smem();
     __syncthreads();
@@ -761,7 +860,10 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         const int y_start = x0;                                 // first frame where any of our rows is on/below the diagonal
         const int y_last = t_y - t_x + x1 - 1;                  // last frame where our last row is inside the band (core.pyx:18)
         const int span = (y_last + 1 - y_start + 31) & ~31;     // whole 32-frame direction words
-        const int y_end = y_start + span + (SKEW ? 32 : 0);     // lane-0 frames; skewed: lane 31 needs 31 more
+        // lane-0 frames; skewed: lane 31 needs 31 more -- with the 4-frame lag the last live lane needs 4 * (lanes - 1) more, and a
+        // lane emits an aligned direction word (lag / 32) + 1 units after lane 0 would
+        const int live_lanes = nrows > 0 ? (nrows + R - 1) / R : 1;
+        const int y_end = y_start + span + (SKEW ? (L4 ? 32 + ((kLag4 * (live_lanes - 1)) & ~31) : 32) : 0);
         const int t_s = y_start / TF, t_e = y_end / TF;         // tiles [t_s, t_e), all whole
 
         if (is_loader) {
@@ -824,7 +926,14 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                         // 16-byte aligned inputs); rows past t_x and frames past T_mel are fetched or zero-filled, never used
                         // The last compute warp of the (padded) text axis is usually only partly filled: it fetches a shorter box
                         // through a second tensor map -- every box row costs TMA engine time (profiles/r01_notes.md).
-                        if (lane == 0) {
+                        if (L4) {
+                            // one pre-skewed box per tile; the utterance's last compute warp goes through the second map, whose lane
+                            // and frame extents stop at the tensor's last row (lanes past it are zero-filled, never fetched)
+                            if (lane == 0) {
+                                mbar_expect_tx(full0 + 8 * stage, RW * TF * ES);
+                                tma_load_3d(st, (gw == NC * NW - 1) ? &tmap_tail : &tmap, t * TF, 0, item * p.Tx + x0, full0 + 8 * stage);
+                            }
+                        } else if (lane == 0) {
                             const bool tail = !VL && (gw == NC * NW - 1) && p.tail_rows < RW;
                             mbar_expect_tx(full0 + 8 * stage, (tail ? p.tail_rows : RW) * TF * ES);
                             if (VL) tma_load_2d(st, &tmap, x0, item * Ty + t * TF, full0 + 8 * stage);      // box = RW tokens x TF frames of [b*t_mel, t_text]
@@ -884,10 +993,11 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             const bool remote_out = (NC > 1 && w == NW - 1 && has_consumer);               // our consumer is warp 0 of the next CTA (has_consumer => there is one)
             const bool lane0 = (lane == 0), lane31 = (lane == 31);
             const int xl0 = x0 + lane * R;
-            const int lag = SKEW ? kSkewLag * lane : 0;
-            const uint32_t bin_addr = bnd_a + w * kRing * 4;           // warp 0 reads the constant sentinel ring: x == 0, y > 0: v_prev = max_neg_val (core.pyx:27)
-            const uint32_t bout_addr = bnd_a + (w + 1) * kRing * 4;
+            const int lag = SKEW ? LAG * lane : 0;
+            const uint32_t bin_addr = bnd_a + w * RING * 4;            // warp 0 reads the constant sentinel ring: x == 0, y > 0: v_prev = max_neg_val (core.pyx:27)
+            const uint32_t bout_addr = bnd_a + (w + 1) * RING * 4;
             const uint32_t my_tail = tail_a + 4 * w, my_head = head_a + 4 * w;
+            const uint32_t prog_addr = lane31 ? my_tail : (lane0 ? my_head : xout_head_a + 4);   // where this lane publishes the unit's end
             const uint32_t in_tail = tail_a + 4 * (w > 0 ? w - 1 : 0);
             const uint32_t out_head = remote_out ? xout_head_a : head_a + 4 * (has_consumer ? w + 1 : w);
             // Cluster hand-off: the producer (last warp of CTA c) writes its local ring as usual and, once per unit, lane 31
@@ -918,14 +1028,16 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             for (int r = 0; r < R; ++r) { S.old[r] = neg; S.wbits[r] = 0u; }
 #pragma unroll
             for (int r = 0; r < R; ++r) S.wprev[r] = 0u;
-            S.up = neg; S.u1 = neg; S.u2 = neg;
+            S.up = neg; S.u1 = neg; S.u2 = neg; S.u3 = neg; S.u4 = neg; S.u5 = neg;
             S.bprev = neg; S.bprev1 = neg;
             if (!has_in) {
                 S.bprev = 0.f;                                      // x == 0, y == 0: v_prev = 0 (core.pyx:25)
             } else {
                 if (CL && remote_in) wait_remote(y_start + UNIT + 32);
-                else wait_flag_ge(in_tail, y_start + UNIT + (SKEW ? 32 : 0), -(1 << 30));
-                if (SKEW) {
+                else wait_flag_ge(in_tail, y_start + UNIT + (SKEW ? (L4 ? 32 * kLag4 : 32) : 0), -(1 << 30));
+                if (L4) {
+                    S.bprev = lds32(bin_addr + (uint32_t)(((y_start + 31 * kLag4 - 1) & (RING - 1)) << 2));   // frame y_start - 1 of the row above
+                } else if (SKEW) {
                     const float4 b = lds128(bin_addr + (((y_start + 28) & (kRing - 1)) << 2));   // frames y_start-4 .. y_start-1 (+31)
                     S.bprev = b.z; S.bprev1 = b.w;
                 } else {
@@ -934,23 +1046,31 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             }
             int seen_cons = has_consumer ? 0 : kProgDone;
             uint32_t prev_stage = 0;
-            constexpr int IN_LEAD = SKEW ? 32 : 0;             // skewed: the producer's lane 31 trails its lane 0 by 31 steps
+            constexpr int IN_LEAD = SKEW ? (L4 ? 32 * kLag4 : 32) : 0;   // skewed: the producer's lane 31 trails its lane 0 by 31 (124) steps
             int seen_in = (has_in && !remote_in) ? y_start + UNIT + IN_LEAD : kProgDone;   // producer progress (in its steps) as last read
             uint32_t* bits_row = bits + xl0;
+            // skewed forms: the block whose aligned word this lane completes in the unit that starts at y_start (a block before the
+            // band for the first unit(s): never dereferenced), advanced by one block row per unit
+            uint32_t* bits_unit = bits_row + ((int64_t)((y_start - 32) >> 5) - (L4 ? (lag >> 5) : 0)) * TXS;
             bool tile_ok = false;                              // next tile's "full" barrier already seen complete
             long long c_full = 0, c_poll = 0, c_unit = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;   // ALB200_DBG cycle breakdown
 
             for (int y = y_start; y < y_end; y += UNIT) {           // y = frame of lane 0
                 const int fin = y & (TF - 1);
                 if (dbg_on) c0 = clock64();
-                if (fin == 0 && !tile_ok) mbar_wait(full0 + 8 * stage, phase);      // (usually already seen complete by the probe below)
+                // our lane 31 is about to overwrite these ring slots (4-frame lag: slots [y - 256, y - 224) were last read by the
+                // consumer's unit y - 256 - 96, finished once its head flag reads y - 320)
+                const int need_in = y + UNIT + IN_LEAD;
+                const int need_cons = L4 ? y + UNIT - RING - 96 : (SKEW ? y + UNIT - 32 - kRing : y + UNIT - (kRing - 4));
+                // In steady state the tile has landed (probe below) and both neighbours were seen far enough along after the last
+                // unit: ONE branch guards the three waits (each wait as its own branch region cost ~40 cycles of the ~260-cycle head).
+                if (!((fin != 0 || tile_ok) && seen_in >= need_in && seen_cons >= need_cons)) {
+                    if (fin == 0 && !tile_ok) mbar_wait(full0 + 8 * stage, phase);
+                    seen_in = wait_flag_ge(in_tail, need_in, seen_in);
+                    seen_cons = wait_flag_ge(out_head, need_cons, seen_cons);
+                }
                 if (dbg_on) c1 = clock64();
                 if (CL && remote_in) wait_remote(y + UNIT + IN_LEAD);
-                seen_in = wait_flag_ge(in_tail, y + UNIT + IN_LEAD, seen_in);
-                {
-                    const int need = SKEW ? y + UNIT - 32 - kRing : y + UNIT - (kRing - 4);   // our lane 31 is about to overwrite these ring slots
-                    seen_cons = wait_flag_ge(out_head, need, seen_cons);
-                }
                 // read now, needed after this unit (latency hidden): both neighbours' progress.  (Probing the next tile's barrier
                 // here with mbarrier.test_wait was measured: the probe itself costs ~800 cycles per unit -- profiles/r01_notes.md.)
                 const int next_in = (has_in && !remote_in) ? ld_flag(in_tail) : kProgDone;
@@ -960,17 +1080,24 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 const uint32_t tile_addr = ring_a + stage * L.stage_bytes + lane * LSTR + fin * ES;
                 const uint32_t tile_prev = (SKEW && y > y_start) ? ring_a + prev_stage * L.stage_bytes + lane * LSTR : tile_addr;
                 const int yl = y - lag;
-                if (y < diag_end)
+                if (L4) {
+                    const uint32_t tile_lane = ring_a + stage * L.stage_bytes + lane * 128;
+                    const uint32_t xs = (uint32_t)(lane & 7) << 4;
+                    if (y < diag_end)
+                        forward_unit4<R, true>(S, tile_lane, xs, bin_addr, bout_addr, y, yl, lane0, lane31, neg, xl0 - yl, bits_unit, y_start, (unsigned)span);
+                    else
+                        forward_unit4<R, false>(S, tile_lane, xs, bin_addr, bout_addr, y, yl, lane0, lane31, neg, 0, bits_unit, y_start, (unsigned)span);
+                } else if (y < diag_end)
                     forward_unit<R, TF, UNIT, SKEW, true, VT, VL>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
-                                                          xl0 - yl, bits_row, TXS, y_start, (unsigned)span);
+                                                          xl0 - yl, bits_row, TXS, y_start, (unsigned)span, bits_unit);
                 else
                     forward_unit<R, TF, UNIT, SKEW, false, VT, VL>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
-                                                           0, bits_row, TXS, y_start, (unsigned)span);
+                                                           0, bits_row, TXS, y_start, (unsigned)span, bits_unit);
+                if (SKEW) bits_unit += TXS;
                 seen_in = next_in;
                 seen_cons = next_cons;
                 if (dbg_on) { c3 = clock64(); c_full += c1 - c0; c_poll += c2 - c1; c_unit += c3 - c2; }
-                if (lane31) st_flag(my_tail, y + UNIT);
-                if (lane0) st_flag(my_head, y + UNIT);
+                st_flag(prog_addr, y + UNIT);        // lane 31 -> tail, lane 0 -> head, the rest -> scratch: one store, no branch
                 if (CL) {
                     if (remote_out && lane31) {                  // ship this unit's 32 boundary values (written by this very lane)
                         const uint32_t off = (uint32_t)(y & (kRing - 1)) << 2;
@@ -982,7 +1109,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                     if (remote_in && lane0) st_cluster_flag(r_head, y + UNIT);
                 }
                 if (((y + UNIT) & (TF - 1)) == 0) {                 // tile consumed: hand the stage back to the loader
-                    if (SKEW) {                                     // the trailing lanes still read this tile during the next unit
+                    if (SKEW && !L4) {                              // the trailing lanes still read this tile during the next unit
                         if (y > y_start) mbar_arrive(empty0 + 8 * prev_stage);
                         prev_stage = stage;
                     } else {
@@ -995,7 +1122,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                     tile_ok = mbar_test_wait(full0 + 8 * stage, phase);
                 }
             }
-            if (SKEW && y_end > y_start) mbar_arrive(empty0 + 8 * prev_stage);
+            if (SKEW && !L4 && y_end > y_start) mbar_arrive(empty0 + 8 * prev_stage);
             if (lane31) st_flag(my_tail, kProgDone);
             if (CL && remote_in) wait_remote(0x3fffffff);          // every incoming copy has landed before this CTA may leave the cluster barrier
             if (dbg_on && first_item && lane == 0) {

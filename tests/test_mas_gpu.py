@@ -113,6 +113,33 @@ def test_differential_small(ma, option, force, kind):
         check_against_oracle(ma, values, t_x, t_y)
 
 
+# The 4-frame-lag form (pre-skewed 3-D TMA boxes, forward_unit4): forced over every instance, one to four compute warps, a
+# partly filled last warp, utterances shorter than the fill, ragged lengths; t_x must be a multiple of the rows per lane.
+@pytest.mark.parametrize("rows,tx,ty", [(2, 64, 96), (2, 40, 400), (2, 200, 640), (2, 256, 300), (3, 96, 2000), (3, 150, 404), (3, 300, 700),
+                                        (4, 128, 128), (4, 200, 1000), (4, 344, 520), (4, 512, 600), (2, 34, 36)])
+@pytest.mark.parametrize("kind", ["gauss", "ties"])
+def test_four_frame_lag_form(ma, option, rows, tx, ty, kind):
+    option("force", "%d,32,0,-1,1,0,4" % rows)
+    assert "form=skewed4" in _lib.describe(3, tx, ty)
+    rng = np.random.default_rng(seed_of("lag4", rows, tx, ty, kind))
+    for trial in range(2):
+        b = int(rng.integers(1, 7))
+        values = make_values(rng, kind, (b, tx, ty))
+        t_x, t_y = random_lengths(rng, b, tx, ty, full=(trial == 0))
+        check_against_oracle(ma, values, t_x, t_y)
+
+
+def test_four_frame_lag_is_chosen_for_one_long_warp(ma):
+    """One compute warp and a long mel axis is where the form measured faster (mas_api.cu, choose_lag4)."""
+    assert "form=skewed4" in _lib.describe(8, 96, 2000)
+    assert "form=skewed4" not in _lib.describe(8, 200, 1000)
+    assert "form=skewed4" not in _lib.describe(8, 95, 2000)          # 95 is not a multiple of 3 rows per lane
+    rng = np.random.default_rng(seed_of("lag4-auto"))
+    values = make_values(rng, "gauss", (5, 96, 2000))
+    t_x, t_y = random_lengths(rng, 5, 96, 2000)
+    check_against_oracle(ma, values, t_x, t_y)
+
+
 @pytest.mark.parametrize("shape,native", [((6, 72, 190), True), ((3, 200, 403), True), ((2, 500, 640), True), ((9, 24, 33), True),
                                           ((6, 70, 190), False),        # t_text % 4 != 0: transposed on the device
                                           ((300, 72, 640), True),       # several SMs' worth: still the skewed form, persistent grid
