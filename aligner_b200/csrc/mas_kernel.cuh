@@ -380,7 +380,7 @@ struct Fwd {
 template <int R, int TF, int UNIT, bool SKEW, bool DIAG, int VT, bool VL>
 __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint32_t tile_prev, uint32_t bin_addr, uint32_t bout_addr, int Y, int yl,
                                              bool lane0, bool lane31, float neg, int dxy, uint32_t* bits_row, int TXS,
-                                             int y_lo, unsigned span, uint32_t* bits_unit)
+                                             int y_lo, unsigned span, uint32_t* bits_unit, bool row0)
 {
     constexpr int NG = UNIT / 4;
     static_assert(!SKEW || UNIT == 32, "the skewed form assembles one direction word per 32-frame unit");
@@ -498,11 +498,19 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
     if (SKEW) {
         // wbits now holds our frames [Y - lane, Y + 32 - lane), wprev the 32 before: the aligned word of block [Y - 32, Y)
         // is the 64-bit window shifted right by `lane`
+        // The skewed forms store the word in the form the backtrack walks it (the lock-step form leaves this to the walker's
+        // window copy): the forced step of the diagonal cell (core.pyx:34, index == y) set -- it can only fall into a DIAG unit --,
+        // token 0 never steps down (index != 0), bit-reversed (frame k at bit 31-k).
         const int yw = Y - 32;
         if ((unsigned)(yw - y_lo) < span) {
             uint32_t* brow = bits_unit;                                   // == bits_row + ((Y - 32) >> 5) * TXS, advanced by the caller
 #pragma unroll
-            for (int r = 0; r < R; ++r) brow[r] = __funnelshift_r(S.wprev[r], S.wbits[r], lane);
+            for (int r = 0; r < R; ++r) {
+                uint32_t wv = __funnelshift_r(S.wprev[r], S.wbits[r], lane);
+                if (DIAG) { const int d = dxy + r + 32 - lane; if ((unsigned)d < 32u) wv |= 1u << d; }     // d = token - first frame of the block
+                if (r == 0 && row0) wv = 0u;
+                brow[r] = __brev(wv);
+            }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) S.wprev[r] = S.wbits[r];
@@ -527,7 +535,7 @@ __device__ __forceinline__ void forward_unit(Fwd<R>& S, uint32_t tile_addr, uint
 // 59.6; this form 21.3 / 25.9 / 28.6.  The price is 4*31 frames of fill per warp instead of 31.
 template <int R, bool DIAG>
 __device__ __forceinline__ void forward_unit4(Fwd<R>& S, uint32_t tile_lane, uint32_t xs, uint32_t bin_addr, uint32_t bout_addr, int Y, int yl,
-                                              bool lane0, bool lane31, float neg, int dxy, uint32_t* bits_unit, int y_lo, unsigned span)
+                                              bool lane0, bool lane31, float neg, int dxy, uint32_t* bits_unit, int y_lo, unsigned span, bool row0)
 {
     constexpr int NG = 8;
     // Boundary ring, indexed by the producer's step: its lane 31 finishes frame f at step f + 124.  Our step Y + kk needs frame
@@ -589,7 +597,12 @@ __device__ __forceinline__ void forward_unit4(Fwd<R>& S, uint32_t tile_lane, uin
     if ((unsigned)(yw - y_lo) < span) {
         uint32_t* brow = bits_unit;                                       // == bits_row + (yw >> 5) * TXS: per-lane base, advanced by the caller
 #pragma unroll
-        for (int r = 0; r < R; ++r) brow[r] = __funnelshift_r(S.wprev[r], S.wbits[r], lagf & 31);
+        for (int r = 0; r < R; ++r) {                                     // final form, as in forward_unit
+            uint32_t wv = __funnelshift_r(S.wprev[r], S.wbits[r], lagf & 31);
+            if (DIAG) { const int d = dxy + r + 32 - (lagf & 31); if ((unsigned)d < 32u) wv |= 1u << d; }
+            if (r == 0 && row0) wv = 0u;
+            brow[r] = __brev(wv);
+        }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) S.wprev[r] = S.wbits[r];
@@ -611,7 +624,7 @@ __device__ __forceinline__ void forward_unit4(Fwd<R>& S, uint32_t tile_lane, uin
 //                                               store them as the shared-memory window of block blk-1;
 //                                           (3) walk block blk through the window stored one iteration ago (broadcast loads).
 //     LD = 2 when the bits live in shared memory, 4 when they come from L2.
-template <int LD>
+template <int LD, bool FINAL>
 __device__ __forceinline__ void backtrack_walk(const uint32_t* bits, int TXS, int t_x, int t_y, int top, int lane, uint32_t win_a,
                                                volatile int* btTok, volatile uint32_t* btMov, uint32_t bt_cur_a, long long* dbg_e)
 {
@@ -634,8 +647,11 @@ __device__ __forceinline__ void backtrack_walk(const uint32_t* bits, int TXS, in
         for (int j = 0; j < NWD; ++j) {
             const int r = a - 32 * j - lane, d = r - yb;
             uint32_t v = wv[j];
-            if (r > 0 && d >= 0 && d < 32) v |= (1u << d);                   // diagonal cell: forced step (index == y)
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wbuf + 4u * (uint32_t)(32 * j + lane)), "r"(__brev(v)) : "memory");
+            if (!FINAL) {                                                        // (the skewed forms store their words patched and reversed)
+                if (r > 0 && d >= 0 && d < 32) v |= (1u << d);                   // diagonal cell: forced step (index == y)
+                v = __brev(v);
+            }
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wbuf + 4u * (uint32_t)(32 * j + lane)), "r"(v) : "memory");
         }
     };
     int tok0 = t_x - 1;
@@ -717,6 +733,67 @@ __device__ __forceinline__ void backtrack_walk(const uint32_t* bits, int TXS, in
             st_flag(bt_cur_a, blk);                           // same lane, after the payload: in-order shared-memory pipe
         }
         anc_cur = anc_next;
+        tok0 -= nmove;
+        if (dbg_e) { const long long q3 = clock64(); bB += q2 - q0; bC += q3 - q2; }
+    }
+    if (dbg_e && lane == 0) { dbg_e[0] = 0; dbg_e[1] = bB / (top + 1); dbg_e[2] = bC / (top + 1); dbg_e[3] = -(top + 1); }
+}
+
+// Direction words in shared memory and already in their final form (skewed forms): the walk reads them where the forward pass put
+// them -- word (block, token) at bits[block * TXS + token], the rows it leaves strictly downwards at descending addresses.  No window
+// copy, no software pipeline: the copy's ~100 instructions per block were what the walker's ~340 cycles per block went to (a lone
+// warp issues one instruction per ~2.4 cycles), not the step chain.  Reads may run a few words below token 0 or into rows whose
+// words were never written; those meet t == 0 (token 0's word is stored as 0) and are never used.
+__device__ __forceinline__ void backtrack_walk_direct(uint32_t bits_a, int TXS, int t_x, int t_y, int top, int lane,
+                                                      volatile int* btTok, volatile uint32_t* btMov, uint32_t bt_cur_a, long long* dbg_e)
+{
+    if (top < 0) return;
+    int tok0 = t_x - 1;
+    long long bB = 0, bC = 0, q0 = 0, q2 = 0;
+    for (int blk = top; blk >= 0; --blk) {
+        if (dbg_e) q0 = clock64();
+        const int yb = blk << 5;
+        const int nvalid = (t_y - yb < 32) ? t_y - yb : 32;
+        uint32_t wadr = bits_a + 4u * (uint32_t)(blk * TXS + tok0);
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(wadr) : "memory");
+        asm volatile("ld.shared.b32 %0, [%1+-4];" : "=r"(w1) : "r"(wadr) : "memory");
+        asm volatile("ld.shared.b32 %0, [%1+-8];" : "=r"(w2) : "r"(wadr) : "memory");
+        asm volatile("ld.shared.b32 %0, [%1+-12];" : "=r"(w3) : "r"(wadr) : "memory");
+        uint32_t moves = 0u;                                                           // bit 31-k: the path steps down going from frame k to k-1
+        const uint32_t below0 = (nvalid < 32) ? ~((1u << (32 - nvalid)) - 1u) : 0xffffffffu;   // (reversed) frames of this block
+        uint32_t t = w0 & below0;
+#define ALB_BT_STEP(T_IN, W_NEXT, T_OUT)                                                                                \
+    {                                                                                                                   \
+        const uint32_t tm = (T_IN) - 1u;                                                                                \
+        moves |= (T_IN) & ~tm;                        /* the step: highest remaining frame = lowest reversed bit */     \
+        T_OUT = (W_NEXT) & ~((T_IN) ^ tm);            /* earlier frames go to the rows further down; 0 ends the block */ \
+    }
+#define ALB_BT_QUAD                                                                                                     \
+        {                                                                                                               \
+            uint32_t t1, t2, t3;                                                                                        \
+            asm volatile("ld.shared.b32 %0, [%1+-16];" : "=r"(w0) : "r"(wadr));                                         \
+            ALB_BT_STEP(t, w1, t1)                                                                                      \
+            asm volatile("ld.shared.b32 %0, [%1+-20];" : "=r"(w1) : "r"(wadr));                                         \
+            ALB_BT_STEP(t1, w2, t2)                                                                                     \
+            asm volatile("ld.shared.b32 %0, [%1+-24];" : "=r"(w2) : "r"(wadr));                                         \
+            ALB_BT_STEP(t2, w3, t3)                                                                                     \
+            asm volatile("ld.shared.b32 %0, [%1+-28];" : "=r"(w3) : "r"(wadr));                                         \
+            ALB_BT_STEP(t3, w0, t)                                                                                      \
+            wadr -= 16u;                                                                                                \
+        }
+        ALB_BT_QUAD
+        ALB_BT_QUAD
+        while (t != 0u) ALB_BT_QUAD
+#undef ALB_BT_QUAD
+#undef ALB_BT_STEP
+        const int nmove = __popc(moves);
+        if (dbg_e) q2 = clock64();
+        if (lane == 0) {
+            btTok[blk] = tok0;
+            btMov[blk] = moves;
+            st_flag(bt_cur_a, blk);                           // same lane, after the payload: in-order shared-memory pipe
+        }
         tok0 -= nmove;
         if (dbg_e) { const long long q3 = clock64(); bB += q2 - q0; bC += q3 - q2; }
     }
@@ -993,6 +1070,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             const bool remote_out = (NC > 1 && w == NW - 1 && has_consumer);               // our consumer is warp 0 of the next CTA (has_consumer => there is one)
             const bool lane0 = (lane == 0), lane31 = (lane == 31);
             const int xl0 = x0 + lane * R;
+            const bool row0 = (xl0 == 0);                      // this lane's first row is token 0
             const int lag = SKEW ? LAG * lane : 0;
             const uint32_t bin_addr = bnd_a + w * RING * 4;            // warp 0 reads the constant sentinel ring: x == 0, y > 0: v_prev = max_neg_val (core.pyx:27)
             const uint32_t bout_addr = bnd_a + (w + 1) * RING * 4;
@@ -1084,15 +1162,15 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                     const uint32_t tile_lane = ring_a + stage * L.stage_bytes + lane * 128;
                     const uint32_t xs = (uint32_t)(lane & 7) << 4;
                     if (y < diag_end)
-                        forward_unit4<R, true>(S, tile_lane, xs, bin_addr, bout_addr, y, yl, lane0, lane31, neg, xl0 - yl, bits_unit, y_start, (unsigned)span);
+                        forward_unit4<R, true>(S, tile_lane, xs, bin_addr, bout_addr, y, yl, lane0, lane31, neg, xl0 - yl, bits_unit, y_start, (unsigned)span, row0);
                     else
-                        forward_unit4<R, false>(S, tile_lane, xs, bin_addr, bout_addr, y, yl, lane0, lane31, neg, 0, bits_unit, y_start, (unsigned)span);
+                        forward_unit4<R, false>(S, tile_lane, xs, bin_addr, bout_addr, y, yl, lane0, lane31, neg, 0, bits_unit, y_start, (unsigned)span, row0);
                 } else if (y < diag_end)
                     forward_unit<R, TF, UNIT, SKEW, true, VT, VL>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
-                                                          xl0 - yl, bits_row, TXS, y_start, (unsigned)span, bits_unit);
+                                                          xl0 - yl, bits_row, TXS, y_start, (unsigned)span, bits_unit, row0);
                 else
                     forward_unit<R, TF, UNIT, SKEW, false, VT, VL>(S, tile_addr, tile_prev, bin_addr, bout_addr, y, yl, lane0, lane31, neg,
-                                                           0, bits_row, TXS, y_start, (unsigned)span, bits_unit);
+                                                           0, bits_row, TXS, y_start, (unsigned)span, bits_unit, row0);
                 if (SKEW) bits_unit += TXS;
                 seen_in = next_in;
                 seen_cons = next_cons;
@@ -1140,10 +1218,14 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         // stores, so address arithmetic and memory traffic are off the serial chain.
         const int top = (crank == 0) ? (t_y - 1) >> 5 : -1;      // cluster: CTA 0 backtracks, the others are done
         if (wid == 0) {
-            if (bits_smem) backtrack_walk<2>(bits, TXS, t_x, t_y, top, lane, smem0 + L.off_ring, btTok, btMov, bt_cur_a,
-                                             kDbgBuild && dbg_on && first_item ? p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4 : nullptr);
-            else           backtrack_walk<4>(bits, TXS, t_x, t_y, top, lane, smem0 + L.off_ring, btTok, btMov, bt_cur_a,
-                                             kDbgBuild && dbg_on && first_item ? p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4 : nullptr);
+            long long* dbg_bt = kDbgBuild && dbg_on && first_item ? p.dbg + (int64_t)gridDim.x * (2 * kMaxWarps + 2) * 2 + ((int64_t)blockIdx.x * kMaxWarps + (kMaxWarps - 1)) * 4 : nullptr;
+            if (SKEW) {     // words stored in their final form
+                if (bits_smem) backtrack_walk_direct(smem0 + L.off_bits, TXS, t_x, t_y, top, lane, btTok, btMov, bt_cur_a, dbg_bt);
+                else           backtrack_walk<4, true>(bits, TXS, t_x, t_y, top, lane, smem0 + L.off_ring, btTok, btMov, bt_cur_a, dbg_bt);
+            } else {
+                if (bits_smem) backtrack_walk<2, false>(bits, TXS, t_x, t_y, top, lane, smem0 + L.off_ring, btTok, btMov, bt_cur_a, dbg_bt);
+                else           backtrack_walk<4, false>(bits, TXS, t_x, t_y, top, lane, smem0 + L.off_ring, btTok, btMov, bt_cur_a, dbg_bt);
+            }
             fence_proxy_async_smem();   // the row windows went through the generic proxy into ring memory that TMA writes next
         } else {
             if (p.frame_tok != nullptr && crank == 0)
