@@ -164,8 +164,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Every wait in this file is bounded: a wrong tensor map or a broken hand-off must surface as a launch error
 // (cudaErrorLaunchFailure at the next synchronisation), never as a hung GPU.  2^26 polls of >= 20 cycles is more than half a
 // second; the longest legitimate wait is a fraction of one utterance's forward pass (milliseconds).
-constexpr uint32_t kSpinLimit = 1u << 26;
+#ifndef ALB_SPIN_LIMIT_LOG2
+#define ALB_SPIN_LIMIT_LOG2 26
+#endif
+constexpr uint32_t kSpinLimit = 1u << ALB_SPIN_LIMIT_LOG2;
+#ifdef ALB_TRAP_PRINT          // developer aid: say which wait gave up (build_lib.py --variant x -DALB_TRAP_PRINT=1 -DALB_SPIN_LIMIT_LOG2=20)
+#include <cstdio>
+#define spin_guard(n) if (++(n) > kSpinLimit) { if ((threadIdx.x & 31) == 0) printf("[alb200] wait at mas_kernel.cuh:%d gave up: block %d thread %d\n", __LINE__, (int)blockIdx.x, (int)threadIdx.x); break; }
+#else
 __device__ __forceinline__ void spin_guard(uint32_t& n) { if (++n > kSpinLimit) __trap(); }
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t n = 0;
     while (!mbar_try_wait(bar, parity)) spin_guard(n);
@@ -879,6 +887,39 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     const float neg = p.neg;
 
     int item = unit_id;
+    // One box load of tile t (frames [t*TF, t*TF+TF)) of the rows of pipeline warp `g` of utterance `it` into stage address st (skewed forms).
+    // The last compute warp of the (padded) text axis is usually only partly filled: it fetches a shorter box through a second
+    // tensor map -- every box row costs TMA engine time (profiles/r01_notes.md).
+    auto issue_tile = [&](int it, int g, int t, uint32_t st, uint32_t bar) {
+        const int xg = g * RW;
+        if (L4) {
+            // one pre-skewed box per tile; the utterance's last compute warp goes through the second map, whose lane and frame
+            // extents stop at the tensor's last row (lanes past it are zero-filled, never fetched)
+            mbar_expect_tx(bar, RW * TF * ES);
+            tma_load_3d(st, (g == NC * NW - 1) ? &tmap_tail : &tmap, t * TF, 0, it * p.Tx + xg, bar);
+        } else {
+            const bool tail = !VL && (g == NC * NW - 1) && p.tail_rows < RW;
+            mbar_expect_tx(bar, (tail ? p.tail_rows : RW) * TF * ES);
+            if (VL) tma_load_2d(st, &tmap, xg, it * p.Ty + t * TF, bar);      // box = RW tokens x TF frames of [b*t_mel, t_text]
+            else tma_load_2d(st, tail ? &tmap_tail : &tmap, t * TF, it * p.Tx + xg, bar);
+        }
+    };
+    // Latency regime, one utterance per CTA: the first two tiles of the first compute warp are requested NOW, before the utterance's
+    // lengths are known (the lengths take one or two dependent global round trips, a first tile ~3000 cycles more): a warp's first
+    // tile only depends on its row offset, and an active warp always consumes at least two.  An inactive warp (empty utterance)
+    // just waits for the two boxes to land before the CTA may exit.
+    int pre = 0;
+#ifndef ALB_EARLY_ALL
+#define ALB_EARLY_ALL 0             // A/B builds: 1 = every loader warp, not only the first (measured: C2 +0.6 %, the later warps have time)
+#endif
+#ifndef ALB_NO_EARLY_TILES
+#define ALB_NO_EARLY_TILES 0        // A/B builds: 1 = off (measured with warp 0 only: C1 25.4 -> 24.4 us, C2 and C3 unchanged)
+#endif
+    if (!ALB_NO_EARLY_TILES && SKEW && NC == 1 && is_loader && p.B <= (int)gridDim.x && p.tile_ready == nullptr && !p.pdl_wait && item < p.B && w * RW < p.Tx && (ALB_EARLY_ALL || w == 0)) {
+        pre = NS < 2 ? NS : 2;
+        if (lane == 0)
+            for (int q = 0; q < pre; ++q) issue_tile(item, w, (w * RW) / TF + q, ring_a + q * L.stage_bytes, full0 + 8 * q);
+    }
     const bool dbg_on = kDbgBuild && (p.dbg != nullptr);     // compiled out of the shipped library (tools/dbg_timing.py builds its own)
     long long* dbg = dbg_on ? p.dbg + (int64_t)blockIdx.x * (2 * kMaxWarps + 2) * 2 : nullptr;
     bool first_item = true;
@@ -990,7 +1031,10 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                 if (p.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // the scores are complete and visible from here on
                 for (int t = t_s; t < t_e; ++t) {
                     if (dbg_on) l0 = clock64();
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1u);      // the compute lanes have released this stage
+                    // the compute lanes have released this stage.  (Not for the tiles requested before the lengths were known: their
+                    // stages were free by construction, and the compute warp may consume such a tile and release its stage before this
+                    // loop gets here -- a parity wait would then wait for a phase that never comes.)
+                    if (t - t_s >= pre) mbar_wait(empty0 + 8 * stage, phase ^ 1u);
                     if (p.tile_ready != nullptr) {                 // scores still being produced: wait for the frames of this tile
                         int need = (t * TF + TF - 1) >> 7;
                         need = need < p.ready_tiles ? need : p.ready_tiles - 1;
@@ -999,23 +1043,9 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                     if (dbg_on) l1 = clock64();
                     const uint32_t st = ring_a + stage * L.stage_bytes;
                     if (SKEW) {
-                        // one 2-D box load per tile: all 32*R rows of this warp x TF frames (the host only picks this form for
-                        // 16-byte aligned inputs); rows past t_x and frames past T_mel are fetched or zero-filled, never used
-                        // The last compute warp of the (padded) text axis is usually only partly filled: it fetches a shorter box
-                        // through a second tensor map -- every box row costs TMA engine time (profiles/r01_notes.md).
-                        if (L4) {
-                            // one pre-skewed box per tile; the utterance's last compute warp goes through the second map, whose lane
-                            // and frame extents stop at the tensor's last row (lanes past it are zero-filled, never fetched)
-                            if (lane == 0) {
-                                mbar_expect_tx(full0 + 8 * stage, RW * TF * ES);
-                                tma_load_3d(st, (gw == NC * NW - 1) ? &tmap_tail : &tmap, t * TF, 0, item * p.Tx + x0, full0 + 8 * stage);
-                            }
-                        } else if (lane == 0) {
-                            const bool tail = !VL && (gw == NC * NW - 1) && p.tail_rows < RW;
-                            mbar_expect_tx(full0 + 8 * stage, (tail ? p.tail_rows : RW) * TF * ES);
-                            if (VL) tma_load_2d(st, &tmap, x0, item * Ty + t * TF, full0 + 8 * stage);      // box = RW tokens x TF frames of [b*t_mel, t_text]
-                            else tma_load_2d(st, tail ? &tmap_tail : &tmap, t * TF, item * p.Tx + x0, full0 + 8 * stage);
-                        }
+                        // one box load per tile: all 32*R rows of this warp x TF frames (the host only picks this form for 16-byte
+                        // aligned inputs); rows past t_x and frames past T_mel are fetched or zero-filled, never used
+                        if (lane == 0 && t - t_s >= pre) issue_tile(item, gw, t, st, full0 + 8 * stage);      // (the first `pre` are already on their way)
                     } else if (p.aligned) {
                         // Loader lane = (16-byte chunk ck of a row, row group q0); it walks the owner lanes li = q0, q0+RPI, ...
                         // and their R rows, so one warp-wide LDGSTS.128 moves RPI whole row segments.
@@ -1058,6 +1088,10 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                     e[0] = l_e; e[1] = l_c; e[2] = l_z; e[3] = t_e - t_s;
                 }
             }
+            if (!active && pre) {                                  // early boxes nobody consumes: landed before this CTA can exit
+                for (int q = 0; q < pre; ++q) mbar_wait(full0 + 8 * q, 0u);
+            }
+            pre = 0;
             if (zf && gw < nact) {
                 issue_zero(0x7fffffff);
                 if (lane == 0) { bulk_commit(); bulk_wait_all(); fence_proxy_async_global(); }
