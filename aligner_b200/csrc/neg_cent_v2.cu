@@ -336,7 +336,7 @@ __device__ __forceinline__ void ota_fast_part(uint32_t tcol, const float4* colv4
     }
     if (nparts > 1) {
         xch[(part * BM + row) * 2] = mx; xch[(part * BM + row) * 2 + 1] = sm;
-        asm volatile("bar.sync 2, 384;" ::: "memory");
+        asm volatile("barrier.sync 2, 384;" ::: "memory");
         float gm = -INFINITY;
         for (int q = 0; q < nparts; ++q) gm = fmaxf(gm, xch[(q * BM + row) * 2]);
         float tot = 0.f;
@@ -632,7 +632,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                 const int q4 = wid & 3, hrow = 32 * q4 + lane, y = mt * BM + hrow;
                 const bool y_ok = y < p.Ty;
                 const float* tokc = reinterpret_cast<const float*>(smem + p.off_aux + 256);
-                asm volatile("bar.sync 2, 384;" ::: "memory");                 // the epilogue warps have staged the per-token terms
+                // (barrier.sync, not bar.sync: bar.sync is the .aligned form, and compute-sanitizer synccheck reports these warps as not
+                //  converged here after the chunk loop's lane-dependent paths; every named barrier of the 384 threads uses this form)
+                asm volatile("barrier.sync 2, 384;" ::: "memory");                 // the epilogue warps have staged the per-token terms
                 mbar_wait(bar_t_full, it & 1u);
                 fence_after();
                 const bool slow = ovf[it & 7] != 0;
@@ -642,11 +644,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                                   (wid - 3) >> 2, 3, hrow, y_ok, p.Tx, p.Ty, p.NT, tlen,
                                   p.prior ? p.prior + (size_t)b * p.Tx * p.Ty + (y_ok ? y : 0) : nullptr, p.out + (size_t)b * p.Tx * p.Ty + (y_ok ? y : 0));
                 else
-                    asm volatile("bar.sync 2, 384;" ::: "memory");             // (the exact path is the epilogue warps' alone; keep the barrier count)
+                    asm volatile("barrier.sync 2, 384;" ::: "memory");             // (the exact path is the epilogue warps' alone; keep the barrier count)
                 fence_before();
                 mbar_arrive(bar_t_empty);
                 if (p.ready != nullptr) __threadfence();
-                asm volatile("bar.sync 2, 384;" ::: "memory");                 // everybody is done with the per-token terms and the partials
+                asm volatile("barrier.sync 2, 384;" ::: "memory");                 // everybody is done with the per-token terms and the partials
             }
         }
     } else {
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                 const float* gc = p.colv + (size_t)b * p.NT;
                 const float* gs = p.inv_sb + (size_t)b * p.NT;
                 for (int i = et; i < p.NT; i += 128) { tokc[i] = __ldg(gc + i); toks[i] = __ldg(gs + i); }
-                if (helpers) asm volatile("bar.sync 2, 384;" ::: "memory");
+                if (helpers) asm volatile("barrier.sync 2, 384;" ::: "memory");
                 else asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             const float4* colv4 = reinterpret_cast<const float4*>(tokc);
@@ -809,7 +811,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
                         }
                     }
                 } else {
-                  if (helpers) asm volatile("bar.sync 2, 384;" ::: "memory");   // the helpers skip an exact tile; keep the barrier count
+                  if (helpers) asm volatile("barrier.sync 2, 384;" ::: "memory");   // the helpers skip an exact tile; keep the barrier count
                   if (y_ok) {
                     // exact fp32 from the raw inputs: squared distance from differences, two passes over the text axis
                     const float T = p.temperature;
@@ -854,7 +856,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nc_v2_kernel(const V2Params p, co
             mbar_arrive(bar_t_empty + 8 * slot);               // 128 arrivals: the accumulator may be overwritten
             if (wid == 11 && lane == 0) NC_STAMP(4, it, 2);
             if (p.ready != nullptr) __threadfence();          // this thread's part of the tile is visible device-wide ...
-            if (helpers) asm volatile("bar.sync 2, 384;" ::: "memory");
+            if (helpers) asm volatile("barrier.sync 2, 384;" ::: "memory");
             else asm volatile("bar.sync 1, 128;" ::: "memory");    // every epilogue thread is done with this tile's per-token terms
             if (p.ready != nullptr && wid == 11 && lane == 0)   // ... before the tile is published to the search running beside us
                 asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.ready + (size_t)b * p.n_mtiles + mt), "r"(p.epoch) : "memory");

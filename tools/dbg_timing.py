@@ -20,5 +20,8 @@ for (b, tx, ty, force) in cases:
         if rep == 1:
             print("== %dx%dx%d force=%s %s" % (b, tx, ty, force, _lib.describe(b, tx, ty)), file=sys.stderr, flush=True)
         _lib.set_option("dbg", "1" if rep == 1 else None)
-        ma.maximum_path_lengths(v, xl, yl, dense=(os.environ.get('DENSE', '1') == '1'), return_frame_tokens=True)
+        if os.environ.get('MASK'):
+            ma.maximum_path(v, torch.ones_like(v) if os.environ['MASK'] == 'f32' else torch.ones(v.shape, dtype=torch.bool, device='cuda'))
+        else:
+            ma.maximum_path_lengths(v, xl, yl, dense=(os.environ.get('DENSE', '1') == '1'), return_frame_tokens=True)
         torch.cuda.synchronize()

@@ -11,11 +11,15 @@ CASES = [(None, 5, 150, 260, torch.float32), ("2,32,2,1,1", 5, 150, 260, torch.f
          ("2,32,2,0,1,2", 3, 300, 420, torch.float32),        # cluster of 2 CTAs per utterance
          ("1,32,3,0,1,4", 2, 500, 520, torch.float32),        # cluster of 4
          (None, 4, 150, 264, torch.bfloat16), (None, 200, 70, 136, torch.float16),     # native half-precision scores: skewed/TMA and throughput forms
-         (None, 200, 70, 133, torch.float32)]                 # throughput regime, unaligned rows
+         (None, 200, 70, 133, torch.float32),                 # throughput regime, unaligned rows
+         ("4,32,0,-1,1,0,4", 4, 200, 1000, torch.float32),    # 4-frame lag, pre-skewed 3-D boxes: two warps, partly filled last warp
+         ("2,32,0,-1,1,0,4", 3, 40, 96, torch.float32),       # ... one warp, tail lanes
+         ("3,32,0,-1,1,0,4", 2, 300, 404, torch.float32),     # ... four warps
+         (None, 6, 130, 140, torch.float32)]                   # two-tile utterances: every tile requested before the lengths are known
 for force, b, tx, ty, dt in CASES:
     _lib.set_option("force", force)
     v = torch.randn(b, tx, ty, device="cuda").to(dt)
-    t_x = rng.integers(1, tx + 1, b).astype(np.int32); t_y = np.array([rng.integers(t_x[i], ty + 1) for i in range(b)], np.int32)
+    t_x = rng.integers(1, min(tx, ty) + 1, b).astype(np.int32); t_y = np.array([rng.integers(t_x[i], ty + 1) for i in range(b)], np.int32)
     out = ma.maximum_path_lengths(v, torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda(), return_durations=True, return_frame_tokens=True)
     torch.cuda.synchronize()
     assert int(out["durations"].sum()) == int(t_y.sum())
