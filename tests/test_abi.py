@@ -54,6 +54,7 @@ def test_sass_uses_bulk_copy_engine(lib_path):
     assert "UBLKCP" in out           # bulk shared->global zero fill
     assert "LDGSTS.E.BYPASS.128" in out  # 128-bit async tile loads (lock-step form)
     assert "UTMALDG.2D" in out       # 2-D TMA box loads (skewed form)
+    assert "UTMALDG.3D" in out       # pre-skewed 3-D boxes (4-frame-lag form) and the score kernel's operand boxes
     assert "SYNCS" in out          # mbarrier ops
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", str(lib_path)], capture_output=True, text=True).stdout
 
