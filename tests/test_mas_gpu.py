@@ -129,6 +129,23 @@ def test_four_frame_lag_form(ma, option, rows, tx, ty, kind):
         check_against_oracle(ma, values, t_x, t_y)
 
 
+def test_two_tile_utterances_on_a_warm_device(ma):
+    """An utterance whose compute warp needs only two tiles: both are requested before its lengths are known, so the compute warp
+    can consume them and release their stages before the loader warp reaches its loop.  (The loader once waited on the stage's
+    "empty" barrier there -- a phase that had already passed: a hang, but only on warm runs; found by the fused shape fuzz.)"""
+    rng = np.random.default_rng(seed_of("two-tile"))
+    for tx, ty in ((130, 704), (64, 96), (200, 1000)):
+        values = make_values(rng, "gauss", (6, tx, ty))
+        t_x = np.array([10, 1, 3, 31, 20, 5], np.int32)
+        t_y = np.array([27, 1, 30, 32, 21, 33], np.int32)          # t_y - t_x + rows <= 32: one 32-frame word, two tiles
+        want = oracle_paths(values, t_x, t_y)
+        v = torch.from_numpy(values).cuda()
+        xl, yl = torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda()
+        for _ in range(40):
+            got = ma.maximum_path_lengths(v, xl, yl)["path"]
+        assert np.array_equal(got.cpu().numpy(), want.astype(np.float32))
+
+
 def test_four_frame_lag_is_chosen_for_one_long_warp(ma):
     """One compute warp and a long mel axis is where the form measured faster (mas_api.cu, choose_lag4)."""
     assert "form=skewed4" in _lib.describe(8, 96, 2000)
