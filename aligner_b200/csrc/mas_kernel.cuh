@@ -30,19 +30,24 @@
 //     warp w-1 through a 128-frame shared ring plus a progress flag, 16 or 32
 //     frames at a time.  The diagonal band provides the pipeline skew for free (warp w
 //     starts at frame 32*R*w); there is no CTA-wide barrier in the forward pass.
-//   * two forward forms, chosen by the host:
+//   * forward forms, chosen by the host:
 //       lock-step  every lane works on the same frame; the neighbour exchange
 //                  (SHFL) sits on the per-frame dependency chain.  No fill cost;
 //                  used when several CTAs share an SM and hide each other.
-//       skewed     lane l runs 4 frames behind lane l-1 (systolic): the shuffle is
-//                  issued four frames before its result is used, so the chain per
-//                  frame is compare-select-add only.  Costs 4 frames of fill per
-//                  lane; used when an utterance has an SM to itself.
+//       skewed     lane l runs ONE frame behind lane l-1 (systolic): the shuffle is
+//                  issued two frames before its result is used.  Tiles arrive as
+//                  one 2-D TMA box per 32 frames; costs 31 frames of fill per warp
+//                  and 32 more per hand-off; used when an utterance has an SM to
+//                  itself (forward_unit).
+//       skewed, 4-frame lag on pre-skewed 3-D boxes (forward_unit4): fewer
+//                  instructions per frame, four times the fill; one long warp only.
 //   * direction bits: shifted into a 32-frame word per row, flushed to shared
 //     memory when it fits, else to an L2-resident per-CTA slot of the workspace.
-//   * backtrack: one warp, 32 frames per step.  Lane l fetches the direction
-//     word of row (tok - l); the words are broadcast and every lane replays the
-//     walk row by row with find-leading-one (one short chain per step down).
+//   * backtrack: one warp walks, 32 frames (one direction word per row) per block,
+//     one add and one 3-input logic op per row visited; the other warps turn the
+//     published (token, step mask) pairs into stores.  The skewed forms store the
+//     words ready to walk and the walker reads them in place when they are in
+//     shared memory; otherwise a software pipeline copies windows of words ahead.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -57,7 +62,6 @@ constexpr int kRing4 = 256;        // ... of the 4-frame-lag form (its consumer 
 constexpr int kLag4 = 4;           // frames lane l trails lane l-1 in the pre-skewed form (the granularity TMA can shift a row by: 16 bytes)
 constexpr int kZeroChunk = 7168;   // bytes per zero-fill bulk store (56 x 128; sized so 2 CTAs x 3 stages still fit an SM at t_x = 400)
 constexpr int kLanePad = 16;       // bytes of skew per lane inside a tile stage
-constexpr int kSkewLag = 1;        // frames lane l trails lane l-1 in the skewed form
 constexpr int kProgDone = 0x3fffffff;
 #ifndef ALB_SPEC_ADD
 #define ALB_SPEC_ADD 1

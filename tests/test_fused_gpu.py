@@ -36,7 +36,8 @@ def _inputs(seed, b, c, tx, ty):
                                        (2, 32, 700, 900),         # t_x > 512: the score kernel takes its fallback path
                                        (130, 64, 90, 400),        # too few SMs left over: back to back
                                        (400, 32, 60, 200),        # throughput regime: back to back
-                                       (4, 40, 70, 261)])         # t_mel % 4 != 0: fallback score kernel
+                                       (4, 40, 70, 261),          # t_mel % 4 != 0: fallback score kernel
+                                       (4, 24, 96, 1600)])        # one compute warp, long mel axis: the search takes its 4-frame-lag form
 def test_fused_equals_separate_calls(mods, b, c, tx, ty, mode):
     fused, ma, nc, _lib = mods
     _lib.set_option("fused_seq", mode)
