@@ -148,7 +148,11 @@ static bool is_latency(const DevInfo& di, int b, int tx, int ty, bool aligned, i
     // utterances, so the mel axis has to be long enough to amortise them
     // (half-precision scores: the lock-step form is the bandwidth-bound one and profits from the halved read -- 4096x200x1000
     //  bf16 1.04 ms lock-step vs 1.18 ms skewed -- so beyond #SM utterances they stay there)
-    if (!aligned || tx > 512 || ty < 600 || vt != 0) return false;
+    // (mel axis: re-measured at the end of round 2, tools/regime_check.sh -- with the cheaper unit and the in-place backtrack the
+    //  persistent skewed form now also wins at 400-600 frames: 300x100x400 50 vs 60 us, 600x300x500 121 vs 138, 1500x160x500 179 vs
+    //  189, 450x400x560 148 vs 156; it still loses at 800x120x360 (99 vs 77), 600x200x300 (109 vs 99) and beyond the batch limits
+    //  below: 4096x160x500 451 vs 441, 3000x130x400 273 vs 257)
+    if (!aligned || tx > 512 || ty < 400 || vt != 0) return false;
     if (tx <= 128) return b <= 3 * di.sms;                       // two compute warps per SM only
     if (tx <= 256) return ty >= 1000 || b <= 12 * di.sms;        // 4096x200x1000: 81.7 % of HBM peak vs 76.7 %
     return b <= 5 * di.sms;

@@ -89,6 +89,8 @@ def main():
         "y2": (2048, 400, 2000, True, [None, "4,32,3,0,1", "4,32,2,0,1", "3,32,3,0,1"]),
         "z1": (4096, 200, 300, False, [None]), "z2": (4096, 160, 500, True, [None]), "z3": (2048, 256, 2000, True, [None]), "z4": (3000, 130, 400, True, [None]),
         "q1": (500, 160, 500, True, [None]), "q2": (400, 100, 300, False, [None]), "q3": (600, 300, 500, True, [None]), "q4": (1000, 200, 640, True, [None]),
+        "r1": (600, 200, 300, False, [None]), "r2": (1000, 300, 500, True, [None]), "r3": (1500, 160, 500, True, [None]), "r4": (300, 100, 400, False, [None]),
+        "r5": (2000, 300, 500, True, [None]), "r6": (450, 400, 560, True, [None]), "r7": (800, 120, 360, False, [None]),
         "c5s": (256, 400, 2000, True, [None, "4,32,2,0,1", "4,32,3,0,1", "4,32,2,0,0"]),
         "c5m": (512, 400, 2000, True, [None, "4,32,2,0,1", "4,32,3,0,1"]),
         "c5l": (1024, 400, 2000, True, [None, "4,32,3,0,1"]),
