@@ -155,6 +155,9 @@ static bool is_latency(const DevInfo& di, int b, int tx, int ty, bool aligned, i
     if (!aligned || tx > 512 || ty < 400 || vt != 0) return false;
     if (tx <= 128) return b <= 3 * di.sms;                       // two compute warps per SM only
     if (tx <= 256) return ty >= 1000 || b <= 12 * di.sms;        // 4096x200x1000: 81.7 % of HBM peak vs 76.7 %
+    // three rows per lane (end of round 2): 1000x300x1500 480 vs 549 us, 2000x300x1500 916 vs 996, 4096x300x1000 1789 vs 1983,
+    // 1000x384x1200 455 vs 499, 2000x300x500 348 vs 369; 3000x320x800 838 vs 828.  Four rows per lane: 1200x512x1500 974 vs 924.
+    if (tx <= 384) return ty >= 1000 || b <= 14 * di.sms;
     return b <= 5 * di.sms;
 }
 static KernelFn find_kernel(int R, int TF, int skew, int nw, int minb, int vt)

@@ -228,6 +228,8 @@ def test_midsize_batch_runs_the_skewed_form_persistently(ma):
         t_x, t_y = random_lengths(rng, b, tx, ty)
         check_against_oracle(ma, values, t_x, t_y)
     assert "form=lockstep" in _lib.describe(4096, 100, 800)             # a full machine's worth of short utterances: occupancy-driven form
+    assert "form=skewed" in _lib.describe(4096, 300, 1000)              # three rows per lane and a long mel axis: persistent skewed form at any batch size
+    assert "form=lockstep" in _lib.describe(4096, 400, 1000)            # four rows per lane: not beyond five SMs' worth
     assert "form=skewed" in _lib.describe(500, 150, 400)                # 400 frames still amortise the pipeline fill (re-measured, mas_api.cu is_latency)
     assert "form=lockstep" in _lib.describe(500, 150, 360)              # shorter mel axis: they do not
 

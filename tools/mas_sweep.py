@@ -91,6 +91,8 @@ def main():
         "q1": (500, 160, 500, True, [None]), "q2": (400, 100, 300, False, [None]), "q3": (600, 300, 500, True, [None]), "q4": (1000, 200, 640, True, [None]),
         "r1": (600, 200, 300, False, [None]), "r2": (1000, 300, 500, True, [None]), "r3": (1500, 160, 500, True, [None]), "r4": (300, 100, 400, False, [None]),
         "r5": (2000, 300, 500, True, [None]), "r6": (450, 400, 560, True, [None]), "r7": (800, 120, 360, False, [None]),
+        "s1": (1000, 300, 1500, True, [None]), "s2": (2000, 300, 1500, True, [None]), "s3": (4096, 300, 1000, False, [None]), "s4": (1000, 384, 1200, True, [None]),
+        "s5": (3000, 320, 800, True, [None]), "s6": (1200, 512, 1500, True, [None]),
         "c5s": (256, 400, 2000, True, [None, "4,32,2,0,1", "4,32,3,0,1", "4,32,2,0,0"]),
         "c5m": (512, 400, 2000, True, [None, "4,32,2,0,1", "4,32,3,0,1"]),
         "c5l": (1024, 400, 2000, True, [None, "4,32,3,0,1"]),
