@@ -16,6 +16,7 @@ struct Opts {
     int nc_v1;             // 1: first-generation tcgen05 score kernels (operands fetched with plain loads)
     int fused_seq;         // fused score + search entry: 1 = always back to back, 2 = pipelined whenever possible (default: by batch size)
     int nc_no_pdl;         // 1: the score kernel waits for the whole prep kernel (no programmatic dependent launch)
+    int no_shared_zero;    // 1: every search CTA zero-fills its own utterance's output (no filler CTAs on the idle SMs)
     unsigned gen;
 };
 const Opts& opts();

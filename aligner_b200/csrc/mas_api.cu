@@ -27,6 +27,7 @@ static int set_opt_locked(const char* name, const char* value)
     else if (!strcmp(name, "latency_max_b")) g_opts.latency_max_b = unset ? -1 : atoi(value);
     else if (!strcmp(name, "tmap_promo")) g_opts.tmap_promo = unset ? -1 : atoi(value);
     else if (!strcmp(name, "no_tail_box")) g_opts.no_tail_box = unset ? 0 : atoi(value) != 0;
+    else if (!strcmp(name, "no_shared_zero")) g_opts.no_shared_zero = unset ? 0 : atoi(value) != 0;
     else if (!strcmp(name, "force_unaligned")) g_opts.force_unaligned = unset ? 0 : atoi(value) != 0;
     else if (!strcmp(name, "dbg")) g_opts.dbg = unset ? 0 : atoi(value);
     else if (!strcmp(name, "nc_ffma")) g_opts.nc_ffma = unset ? 0 : atoi(value) != 0;
@@ -42,7 +43,7 @@ static void opts_from_env()
     memset(&g_opts, 0, sizeof(g_opts));
     g_opts.latency_max_b = -1; g_opts.tmap_promo = -1;
     static const char* const names[][2] = { {"ALB200_FORCE", "force"}, {"ALB200_LATENCY_MAX_B", "latency_max_b"}, {"ALB200_TMAP_PROMO", "tmap_promo"},
-        {"ALB200_NO_TAIL_BOX", "no_tail_box"}, {"ALB200_FORCE_UNALIGNED", "force_unaligned"}, {"ALB200_DBG", "dbg"}, {"ALB200_NC_FFMA", "nc_ffma"},
+        {"ALB200_NO_TAIL_BOX", "no_tail_box"}, {"ALB200_NO_SHARED_ZERO", "no_shared_zero"}, {"ALB200_FORCE_UNALIGNED", "force_unaligned"}, {"ALB200_DBG", "dbg"}, {"ALB200_NC_FFMA", "nc_ffma"},
         {"ALB200_NC_V1", "nc_v1"}, {"ALB200_NC_NO_PDL", "nc_no_pdl"}, {"ALB200_FUSED_SEQ", "fused_seq"} };
     for (auto& n : names)
         if (const char* e = getenv(n[0])) set_opt_locked(n[1], e[0] ? e : "1");
@@ -494,9 +495,28 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
     }
     p.neg = neg;
     p.tile_ready = tile_ready; p.ready_epoch = ready_epoch; p.ready_tiles = ready_tiles; p.pdl_wait = pdl_wait;
+    // Shared zero fill (mas_kernel.cuh): fewer utterances than SMs, one CTA each, a plain launch, 16-byte aligned output -- pad the
+    // grid with filler CTAs for the idle SMs.
+    int fillers = 0;
+    {
+        const int64_t total = (int64_t)b * tx * ty * esize;
+        // (A/B on one box, us, own fill / shared: C3 32x300x1500 68.6 / 61.5; C2 64x200x1000 38.3 / 38.9; C1 16x100x800 24.0 / 25.1 -- it pays
+        //  when one utterance's output takes an SM longer to zero than its forward pass takes: from about 1 KB per frame)
+        if (paths && zero_fill && !opts().no_shared_zero && (int64_t)tx * esize >= 1000 && c.nc == 1 && b <= c.grid && c.grid < di.sms && tile_ready == nullptr && !pdl_wait &&
+            (reinterpret_cast<uintptr_t>(paths) & 15) == 0 && total % 16 == 0 && total / kZeroChunk < 0x3fffffff) {
+            int occ = 0;
+            ALB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c.fn, 2 * c.NW * 32, c.smem));
+            if (occ == 1) {                              // (one CTA per SM: the fillers land on the idle SMs, not beside a search CTA)
+                p.zero_chunks = (int)((total + kZeroChunk - 1) / kZeroChunk);
+                p.search_ctas = c.grid;
+                const int want = (p.zero_chunks + 63) / 64;
+                fillers = di.sms - c.grid < want ? di.sms - c.grid : want;
+            }
+        }
+    }
     static long long* d_dbg = nullptr;
     const bool dbg = kDbgBuild && opts().dbg == 1;
-    const size_t dbg_n = (size_t)c.grid * ((2 * kMaxWarps + 2) * 2 + kMaxWarps * 8);
+    const size_t dbg_n = (size_t)(c.grid + fillers) * ((2 * kMaxWarps + 2) * 2 + kMaxWarps * 8);
     if (dbg) {   // developer aid: per-warp clock64 stamps of the first item of every CTA, printed to stderr
         if (d_dbg) cudaFree(d_dbg);
         ALB_CUDA(cudaMalloc(&d_dbg, dbg_n * 8));
@@ -527,7 +547,7 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
         lc.attrs = at; lc.numAttrs = na;
         ALB_CUDA(cudaLaunchKernelExC(&lc, (const void*)c.fn, args));
     } else {
-        ALB_CUDA(cudaLaunchKernel((const void*)c.fn, dim3(c.grid), dim3(2 * c.NW * 32), args, c.smem, stream));
+        ALB_CUDA(cudaLaunchKernel((const void*)c.fn, dim3(c.grid + fillers), dim3(2 * c.NW * 32), args, c.smem, stream));
     }
     ++g_launches;
     if (dbg) {
@@ -690,7 +710,7 @@ size_t alb200_fused_workspace_bytes(int b, int c, int tx, int ty)
 {
     const size_t nc = alb200_neg_cent_workspace_bytes(0, b, c, tx, ty);
     const size_t flags = ((size_t)b * ((ty + 127) / 128) * 4 + 1024 + 255) & ~(size_t)255;     // + slack for the developer time stamps
-    return ((nc + 255) & ~(size_t)255) + flags + alb200_mas_workspace_bytes(b, tx, ty);
+    return ((nc + 255) & ~(size_t)255) + flags + ((alb200_mas_workspace_bytes(b, tx, ty) + 255) & ~(size_t)255);
 }
 
 int alb200_gaussian_mas_fused(const float* z, const float* m_p, const float* logs_p, float* neg_cent, const int32_t* t_xs, const int32_t* t_ys,
@@ -706,10 +726,13 @@ int alb200_gaussian_mas_fused(const float* z, const float* m_p, const float* log
     const size_t nc_bytes = (alb200_neg_cent_workspace_bytes(0, b, c, tx, ty) + 255) & ~(size_t)255;
     const int n_mt = (ty + 127) / 128;
     const size_t flag_bytes = ((size_t)b * n_mt * 4 + 1024 + 255) & ~(size_t)255;
-    char* ws = reinterpret_cast<char*>(workspace);
+    // Layout: [search workspace][score scratch][tile flags].  The search's 64-byte header comes FIRST so that it stays where it is
+    // from call to call whatever the shapes: its counters re-arm themselves and rely on the zero-initialised buffer, which a header
+    // at a shape-dependent offset (inside what an earlier call used as score scratch) would not have.
+    const size_t mas_ws_bytes = (alb200_mas_workspace_bytes(b, tx, ty) + 255) & ~(size_t)255;
+    void* mas_ws = workspace;
+    char* ws = reinterpret_cast<char*>(workspace) + mas_ws_bytes;       // score scratch
     int* flags = reinterpret_cast<int*>(ws + nc_bytes);
-    void* mas_ws = ws + nc_bytes + flag_bytes;
-    const size_t mas_ws_bytes = workspace_bytes - nc_bytes - flag_bytes;
     DevInfo di;
     int rc = device_info(&di);
     if (rc) return rc;

@@ -78,7 +78,10 @@ struct WsHeader {       // first 64 bytes of the workspace
     int counter;        // work-stealing cursor (self-resetting)
     int done;           // CTAs that left the item loop
     int status;         // bit0: invalid lengths seen
-    int pad[13];
+    int zero_cursor;    // shared zero fill: next unclaimed chunk of the dense output (self-resetting, like the two below)
+    int zero_done;      // ... chunks whose zeros are in global memory
+    int zero_exit;      // ... CTAs (search + filler) that have left the kernel
+    int pad[10];
 };
 
 struct MasParams {
@@ -112,6 +115,8 @@ struct MasParams {
     int aligned;                // values base and Ty allow 16-byte copies
     int nc;                     // CTAs per utterance (thread-block cluster; 1 = one CTA per utterance)
     int tail_rows;              // skewed form: token rows in the box of the LAST compute warp of the utterance (second tensor map)
+    int search_ctas;            // shared zero fill (latency regime, fewer utterances than SMs): CTAs [0, search_ctas) align, the rest of the
+    int zero_chunks;            //   grid only zero-fills; zero_chunks = kZeroChunk-sized pieces of the whole dense output (0 = every CTA fills its own utterance)
     float neg;
     uint32_t off_full, off_empty, off_xbar, off_flags, off_misc, off_bnd, off_zero, off_ring, off_bits, off_dur, off_bt, stage_bytes;   // make_layout(), done on the host
 };
@@ -913,6 +918,55 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
     // tile only depends on its row offset, and an active warp always consumes at least two.  An inactive warp (empty utterance)
     // just waits for the two boxes to land before the CTA may exit.
     int pre = 0;
+    // Shared zero fill.  In the latency regime the dense output is B x t_text x t_mel zeros written by B of the 148 SMs, and one SM's bulk
+    // stores drain at ~30 GB/s: on C3 (32 utterances, 57.6 MB) that is as long as the whole search, and the scatter of the ones has to
+    // wait for it (measured without the dense output: C2 41.4 -> 37.3 us, C3 70.1 -> 55.8, C4 293 -> 263).  So the grid is padded with
+    // filler CTAs on the idle SMs that only zero-fill: every loader warp of every CTA claims batches of 7 KB chunks of the WHOLE
+    // output from one cursor in the workspace header, and a search CTA scatters its ones once all chunks are reported done.
+    // Deadlock-free without any co-residency assumption: a CTA that never starts never claims, and the search CTAs' own loaders keep
+    // claiming until the cursor is exhausted.
+    const bool sz = p.zero_chunks > 0;
+    constexpr int kZeroBatch = 4;
+    int sz_mine = 0;                                                  // chunks this thread issued
+    auto sz_claim = [&](int batches) {                               // (lane 0 of a warp)
+        unsigned char* zb = reinterpret_cast<unsigned char*>(p.paths);
+        const int64_t total = (int64_t)p.B * p.Tx * p.Ty * p.esize;
+        for (int q = 0; q < batches; ++q) {
+            const int first = atomicAdd(&p.ws->zero_cursor, kZeroBatch);
+            if (first >= p.zero_chunks) return false;
+            for (int k = first; k < first + kZeroBatch && k < p.zero_chunks; ++k) {
+                const int64_t off = (int64_t)k * kZeroChunk, left = total - off;
+                bulk_s2g(zb + off, smem_u32(smem + p.off_zero), (uint32_t)(left < kZeroChunk ? left : kZeroChunk));
+                ++sz_mine;
+            }
+        }
+        return true;
+    };
+    auto sz_report = [&]() {                                          // (lane 0 of a warp) everything this thread issued is in global memory
+        if (sz_mine) {
+            bulk_commit(); bulk_wait_all(); fence_proxy_async_global();
+            __threadfence();
+            atomicAdd(&p.ws->zero_done, sz_mine);
+            sz_mine = 0;
+        }
+    };
+    auto sz_leave = [&]() {                                           // (one thread per CTA) the last CTA out re-arms the counters
+        const int d = atomicAdd(&p.ws->zero_exit, 1);
+        if (d == (int)gridDim.x - 1) { p.ws->zero_cursor = 0; p.ws->zero_done = 0; p.ws->zero_exit = 0; __threadfence(); }
+    };
+    if (sz && (int)blockIdx.x >= p.search_ctas) {                     // ---- filler CTA
+        for (int i = threadIdx.x; i < kZeroChunk / 16; i += blockDim.x)
+            reinterpret_cast<int4*>(smem + p.off_zero)[i] = make_int4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) {
+            while (sz_claim(1)) { }
+            sz_report();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) sz_leave();
+        return;
+    }
 #ifndef ALB_EARLY_ALL
 #define ALB_EARLY_ALL 0             // A/B builds: 1 = every loader warp, not only the first (measured: C2 +0.6 %, the later warps have time)
 #endif
@@ -990,7 +1044,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
 
         if (is_loader) {
             // ================= loader warp: tile stream + fused zero fill =================
-            const bool zf = p.zero_fill && p.paths != nullptr;
+            const bool zf = p.zero_fill && p.paths != nullptr && !sz;        // (shared zero fill: claimed from the global cursor instead)
             unsigned char* pbase = reinterpret_cast<unsigned char*>(p.paths) + item * item_elems * p.esize;
             unsigned char* zA = nullptr;
             int64_t zbytes = 0;
@@ -1084,7 +1138,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
                     }
                     if (++stage == (uint32_t)NS) { stage = 0; phase ^= 1u; }
                     if (dbg_on) l2 = clock64();
-                    if (zf) issue_zero(zq);
+                    if (zf) issue_zero(zq);          // (shared zero fill: the filler CTAs do it meanwhile; a claim here is a global atomic round trip per tile)
                     if (dbg_on) { const long long l3 = clock64(); l_e += l1 - l0; l_c += l2 - l1; l_z += l3 - l2; }
                 }
                 if (dbg_on && first_item && lane == 0) {
@@ -1099,6 +1153,10 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
             if (zf && gw < nact) {
                 issue_zero(0x7fffffff);
                 if (lane == 0) { bulk_commit(); bulk_wait_all(); fence_proxy_async_global(); }
+            }
+            if (sz && lane == 0) {                                 // whatever the fillers have not taken by now, then report
+                while (sz_claim(1)) { }
+                sz_report();
             }
         } else if (active) {
             // ================= compute warp: forward pass for rows [x0, x1) =================
@@ -1249,6 +1307,19 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         if (dbg_on && first_item && lane == 0) dbg[wid * 2 + 1] = clock64();
         if (NC > 1) cluster_sync_all();      // all CTAs' direction bits (L2 slot) and zero fill are complete and visible
         else __syncthreads();
+        if (sz) {                            // shared zero fill: the ones may only be scattered once every chunk of zeros has landed
+            if (tid == 0) {
+                uint32_t n = 0;
+                for (;;) {
+                    int done;
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(&p.ws->zero_done) : "memory");
+                    if (done >= p.zero_chunks) break;
+                    __nanosleep(100);
+                    spin_guard(n);
+                }
+            }
+            __syncthreads();
+        }
 
         // ================= backtrack =================
         // Warp 0 walks: 32 frames per step, one find-leading-one chain per step DOWN (about t_x/t_y of the frames).  It only
@@ -1303,6 +1374,7 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, MINB) mas_kernel(const MasPara
         unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         atomicMax(reinterpret_cast<unsigned long long*>(const_cast<int*>(p.tile_ready) + (int64_t)p.B * p.ready_tiles + 64) + 3, gt);
     }
+    if (sz && tid == 0) sz_leave();
     if (NC == 1 && p.B > (int)gridDim.x && tid == 0) {
         const int d = atomicAdd(&p.ws->done, 1);
         if (d == (int)gridDim.x - 1) {      // last CTA out re-arms the counters for the next launch

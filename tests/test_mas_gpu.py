@@ -129,6 +129,28 @@ def test_four_frame_lag_form(ma, option, rows, tx, ty, kind):
         check_against_oracle(ma, values, t_x, t_y)
 
 
+@pytest.mark.parametrize("shape", [(6, 300, 640), (3, 500, 644), (20, 256, 400), (2, 400, 1500)])
+def test_shared_zero_fill(ma, option, shape):
+    """Fewer utterances than SMs and a big dense output: filler CTAs on the idle SMs zero the whole output from a shared cursor and the
+    search CTAs scatter their ones only after every chunk is reported done.  Same paths as with every CTA filling its own
+    utterance, for repeated launches (the counters in the workspace header re-arm themselves), empty utterances included."""
+    b, tx, ty = shape
+    rng = np.random.default_rng(seed_of("shared-zero", shape))
+    values = make_values(rng, "gauss", (b, tx, ty))
+    t_x, t_y = random_lengths(rng, b, tx, ty)
+    if b > 2:
+        t_x[1] = 0
+    want = oracle_paths(values, t_x, t_y)
+    v = torch.from_numpy(values).cuda()
+    xl, yl = torch.from_numpy(t_x).cuda(), torch.from_numpy(t_y).cuda()
+    for own in (None, "1", None):
+        option("no_shared_zero", own)
+        for _ in range(10):
+            out = torch.full((b, tx, ty), 7.0, device="cuda")          # the kernel must overwrite every cell
+            got = ma.maximum_path_lengths(v, xl, yl)["path"]
+        assert np.array_equal(got.cpu().numpy(), want.astype(np.float32)), own
+
+
 def test_two_tile_utterances_on_a_warm_device(ma):
     """An utterance whose compute warp needs only two tiles: both are requested before its lengths are known, so the compute warp
     can consume them and release their stages before the loader warp reaches its loop.  (The loader once waited on the stage's
