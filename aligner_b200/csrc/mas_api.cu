@@ -502,7 +502,7 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
         const int64_t total = (int64_t)b * tx * ty * esize;
         // (A/B on one box, us, own fill / shared: C3 32x300x1500 68.6 / 61.5; C2 64x200x1000 38.3 / 38.9; C1 16x100x800 24.0 / 25.1 -- it pays
         //  when one utterance's output takes an SM longer to zero than its forward pass takes: from about 1 KB per frame)
-        if (paths && zero_fill && !opts().no_shared_zero && (int64_t)tx * esize >= 1000 && c.nc == 1 && b <= c.grid && c.grid < di.sms && tile_ready == nullptr && !pdl_wait &&
+        if (paths && zero_fill && !opts().no_shared_zero && (int64_t)tx * esize >= 1000 && (int64_t)b * c.nc <= c.grid && c.grid < di.sms && tile_ready == nullptr && !pdl_wait &&
             (reinterpret_cast<uintptr_t>(paths) & 15) == 0 && total % 16 == 0 && total / kZeroChunk < 0x3fffffff) {
             int occ = 0;
             ALB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c.fn, 2 * c.NW * 32, c.smem));
@@ -511,6 +511,8 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
                 p.search_ctas = c.grid;
                 const int want = (p.zero_chunks + 63) / 64;
                 fillers = di.sms - c.grid < want ? di.sms - c.grid : want;
+                fillers -= fillers % c.nc;                   // cluster launches: whole filler clusters
+                if (fillers == 0) { p.zero_chunks = 0; p.search_ctas = 0; }
             }
         }
     }
@@ -527,7 +529,7 @@ static int launch_mas(const void* values, const int32_t* t_xs, const int32_t* t_
     if (c.nc > 1 || tile_ready != nullptr || pdl_wait) {
         cudaLaunchConfig_t lc;
         memset(&lc, 0, sizeof(lc));
-        lc.gridDim = dim3(c.grid); lc.blockDim = dim3(2 * c.NW * 32); lc.dynamicSmemBytes = c.smem; lc.stream = stream;
+        lc.gridDim = dim3(c.grid + fillers); lc.blockDim = dim3(2 * c.NW * 32); lc.dynamicSmemBytes = c.smem; lc.stream = stream;
         cudaLaunchAttribute at[2];
         int na = 0;
         if (c.nc > 1) {
