@@ -15,7 +15,8 @@ CASES = [(None, 5, 150, 260, torch.float32), ("2,32,2,1,1", 5, 150, 260, torch.f
          ("4,32,0,-1,1,0,4", 4, 200, 1000, torch.float32),    # 4-frame lag, pre-skewed 3-D boxes: two warps, partly filled last warp
          ("2,32,0,-1,1,0,4", 3, 40, 96, torch.float32),       # ... one warp, tail lanes
          ("3,32,0,-1,1,0,4", 2, 300, 404, torch.float32),     # ... four warps
-         (None, 6, 130, 140, torch.float32)]                   # two-tile utterances: every tile requested before the lengths are known
+         (None, 6, 130, 140, torch.float32),                  # two-tile utterances: every tile requested before the lengths are known
+         (None, 5, 300, 400, torch.float32), (None, 2, 600, 700, torch.float32)]     # shared zero fill: filler CTAs, filler clusters
 for force, b, tx, ty, dt in CASES:
     _lib.set_option("force", force)
     v = torch.randn(b, tx, ty, device="cuda").to(dt)
